@@ -1,0 +1,402 @@
+"""
+Host-side mirror of the reference's engine interface
+(src/cuda_policy_iteration.py of nicoRomeroCuruchet/DynamicProgramming):
+
+    CudaPIConfig                        :36-43
+    CudaPolicyIteration2D / 4D / 6D     :46, :439, :847
+
+Same constructor, same abstract plugin hooks (`_dynamics_cuda_src`,
+`_terminal_fn`), same methods (`policy_evaluation`, `policy_improvement`,
+`run`, `save`, `load`) and the same public attributes, so an environment class
+written for the reference subclasses these unchanged.  Underneath, every
+method is a call into libdpb200.so (hand-written sm_100a CUDA behind the C ABI
+of include/dpb200.h).  There is no CPU path: constructing an engine without a
+CUDA device raises RuntimeError, like the reference does without cupy (:71-75).
+"""
+from __future__ import annotations
+
+import abc
+import ctypes as C
+import os
+from dataclasses import dataclass
+from itertools import product
+from pathlib import Path
+
+import numpy as np
+
+from . import _ffi
+
+try:  # the reference logs through loguru; keep the same sink when present
+    from loguru import logger
+except ImportError:  # pragma: no cover
+    import logging
+
+    class _Shim:
+        _l = logging.getLogger("dynamicprogramming_b200")
+
+        def debug(self, m): self._l.debug(m)
+        def info(self, m): self._l.info(m)
+        def success(self, m): self._l.info(m)
+        def warning(self, m): self._l.warning(m)
+
+    logger = _Shim()
+
+
+@dataclass
+class CudaPIConfig:
+    """Same fields and defaults as the reference (src/cuda_policy_iteration.py:36-43)."""
+    gamma: float = 0.99
+    theta: float = 1e-4
+    max_eval_iter: int = 10_000
+    max_pi_iter: int = 50
+    log_interval: int = 100
+
+
+# states above which `_terminal_fn` is evaluated slab by slab instead of on the
+# fully materialised (N, D) array (host memory / time; results are identical
+# for the element-wise masks every reference environment uses).
+_CHUNK_STATES = int(os.environ.get("DPB200_TERMINAL_CHUNK", 16_000_000))
+
+
+class DeviceArray:
+    """Non-owning handle on an engine device buffer (the `d_*` attributes of the
+    reference object).  Exposes __cuda_array_interface__ so torch / cupy can
+    wrap it zero-copy: ``torch.as_tensor(pi.d_value_function, device="cuda")``."""
+
+    def __init__(self, ptr: int, shape: tuple, typestr: str, owner) -> None:
+        self._ptr, self.shape, self._typestr, self._owner = ptr, shape, typestr, owner
+
+    @property
+    def __cuda_array_interface__(self) -> dict:
+        return {"shape": self.shape, "typestr": self._typestr, "data": (self._ptr, False), "version": 3,
+                "strides": None}
+
+    def torch(self):
+        import torch
+        return torch.as_tensor(self, device=f"cuda:{self._owner._device}")
+
+    def get(self) -> np.ndarray:
+        return self.torch().cpu().numpy()
+
+
+class _CudaPolicyIterationBase(abc.ABC):
+    """Dimension-generic implementation behind the 2D/4D/6D classes."""
+
+    N_DIMS: int = 0
+
+    def __init__(self, bins_space: dict, action_space: np.ndarray, config: CudaPIConfig | None = None,
+                 *, device: int | None = None, shard: tuple | None = None) -> None:
+        _ffi.lib()  # raises if the CUDA extension is missing
+        self.config = config or CudaPIConfig()
+        self.action_space = np.ascontiguousarray(action_space, dtype=np.float32)
+        self.n_actions = len(self.action_space)
+
+        keys = list(bins_space.keys())
+        assert len(keys) == self.N_DIMS, (
+            f"CudaPolicyIteration{self.N_DIMS}D requires exactly {self.N_DIMS} state dimensions."
+        )
+        # per-axis node coordinates: the float32 bits the reference stores in states_space columns
+        self._axes = [np.ascontiguousarray(np.asarray(bins_space[k]).astype(np.float32)) for k in keys]
+        self._axis_names = keys
+        self.n_states = int(np.prod([len(a) for a in self._axes], dtype=np.int64))
+        self._states_space = None
+        self._device = int(os.environ.get("LOCAL_RANK", 0)) if device is None else int(device)
+        self._shard = shard  # (rank, world_size, nccl_id bytes)
+        self._engine = None
+        self._table_ready = False
+        self._log_cb = None
+
+        self._precompute_grid_metadata()
+        self._allocate_tensors_and_compile()
+
+    # ── Grid metadata (src/cuda_policy_iteration.py:95-109, :497-514, :912-937) ──
+
+    @property
+    def states_space(self) -> np.ndarray:
+        """(n_states, D) float32, row-major, dim 0 slowest — materialised on first use
+        (the reference builds it eagerly with meshgrid(indexing="ij") + column_stack)."""
+        if self._states_space is None:
+            grids = np.meshgrid(*self._axes, indexing="ij")
+            self._states_space = np.column_stack([g.ravel() for g in grids]).astype(np.float32)
+        return self._states_space
+
+    @states_space.setter
+    def states_space(self, value) -> None:
+        self._states_space = value
+
+    def _precompute_grid_metadata(self) -> None:
+        D = self.N_DIMS
+        # min / max / unique over a column of the meshgrid equal the same over its axis
+        self.bounds_low = np.array([a.min() for a in self._axes], dtype=np.float32)
+        self.bounds_high = np.array([a.max() for a in self._axes], dtype=np.float32)
+        self.grid_shape = np.array([len(np.unique(a)) for a in self._axes], dtype=np.int32)
+        for d, a in enumerate(self._axes):
+            if self.grid_shape[d] != len(a):
+                raise ValueError(f"bins_space[{self._axis_names[d]!r}] contains duplicate nodes")
+        strides = np.ones(D, dtype=np.int64)
+        for d in range(D - 2, -1, -1):
+            strides[d] = strides[d + 1] * self.grid_shape[d + 1]
+        self.strides = strides.astype(np.int32)
+        self.corner_bits = np.array(list(product([0, 1], repeat=D)), dtype=np.int32)
+        logger.info(f"Grid: shape={self.grid_shape.tolist()}, states={self.n_states:,}, actions={self.n_actions}")
+
+    # ── Plugin interface (identical to the reference) ─────────────────────────
+
+    @abc.abstractmethod
+    def _dynamics_cuda_src(self) -> str:
+        """CUDA source defining
+            __device__ void step_dynamics(float s0, ..., float s{D-1}, float action,
+                                          float* ns0, ..., float* ns{D-1},
+                                          float* reward, bool* terminated)
+        (src/cuda_policy_iteration.py:113-125, :518-530, :941-954)."""
+
+    def _terminal_fn(self, states: np.ndarray) -> tuple[np.ndarray, float]:
+        """(bool mask over states, terminal value); default: none (:127-138)."""
+        return np.zeros(len(states), dtype=bool), 0.0
+
+    # ── Device allocation & compilation (:142-175) ─────────────────────────────
+
+    def _terminal_mask_and_value(self) -> tuple[np.ndarray, float]:
+        if type(self)._terminal_fn is _CudaPolicyIterationBase._terminal_fn:
+            return np.zeros(self.n_states, dtype=bool), 0.0
+        if self.n_states <= _CHUNK_STATES:
+            mask, value = self._terminal_fn(self.states_space)
+            return np.asarray(mask, dtype=bool), float(value)
+        # slab-wise over dim 0
+        inner = self.n_states // len(self._axes[0])
+        rest = np.meshgrid(*self._axes[1:], indexing="ij")
+        rest_cols = [g.ravel() for g in rest]
+        mask = np.empty(self.n_states, dtype=bool)
+        value = 0.0
+        for i, x0 in enumerate(self._axes[0]):
+            chunk = np.column_stack([np.full(inner, x0, dtype=np.float32)] + rest_cols).astype(np.float32)
+            m, value = self._terminal_fn(chunk)
+            mask[i * inner:(i + 1) * inner] = m
+        return mask, float(value)
+
+    def _allocate_tensors_and_compile(self) -> None:
+        logger.info("Allocating GPU tensors and compiling CUDA kernels...")
+        lib = _ffi.lib()
+        D = self.N_DIMS
+        grid = _ffi.PiGrid()
+        grid.n_dims = D
+        for d in range(D):
+            grid.shape[d] = int(self.grid_shape[d])
+            grid.lo[d] = float(self.bounds_low[d])
+            grid.hi[d] = float(self.bounds_high[d])
+            grid.axes[d] = self._axes[d].ctypes.data_as(C.POINTER(C.c_float))
+        cfg = _ffi.PiConfig(float(self.config.gamma), float(self.config.theta), int(self.config.max_eval_iter),
+                            int(self.config.max_pi_iter), int(self.config.log_interval), 25)
+        shard_p = None
+        if self._shard is not None and self._shard[1] > 1:
+            sh = _ffi.PiShard()
+            sh.rank, sh.world_size = int(self._shard[0]), int(self._shard[1])
+            C.memmove(sh.nccl_id, bytes(self._shard[2]), 128)
+            shard_p = C.byref(sh)
+        handle = C.c_void_p()
+        _ffi.check(lib.pi_create(C.byref(grid), self.action_space.ctypes.data_as(C.POINTER(C.c_float)),
+                                 self.n_actions, C.byref(cfg), self._dynamics_cuda_src().encode(), self._device,
+                                 shard_p, C.byref(handle)))
+        self._engine = handle
+
+        levels = {0: logger.debug, 1: logger.info, 2: logger.success, 3: logger.warning}
+        self._log_cb = _ffi.LOG_FN(lambda lvl, msg, _u: levels.get(lvl, logger.info)(msg.decode(errors="replace")))
+        _ffi.check(lib.pi_set_log(self._engine, self._log_cb, None))
+
+        terminal_mask, terminal_value = self._terminal_mask_and_value()
+        self._terminal_mask_host = np.ascontiguousarray(terminal_mask, dtype=np.uint8)
+        if self._terminal_mask_host.any():
+            _ffi.check(lib.pi_set_terminal(self._engine, _ffi.ptr(self._terminal_mask_host), float(terminal_value)))
+            logger.info(f"Terminal states: {int(terminal_mask.sum()):,} (value={terminal_value})")
+        self._refresh_device_handles()
+        logger.success("CUDA kernels compiled. VRAM allocated.")
+
+    def _refresh_device_handles(self) -> None:
+        lib = _ffi.lib()
+        v, nv, pol, term = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _ffi.check(lib.pi_device_ptrs(self._engine, C.byref(v), C.byref(nv), C.byref(pol), C.byref(term)))
+        n_local = lib.pi_local_end(self._engine) - lib.pi_local_begin(self._engine)
+        self.d_value_function = DeviceArray(v.value, (self.n_states,), "<f4", self)
+        self.d_new_value_function = DeviceArray(nv.value, (self.n_states,), "<f4", self)
+        self.d_policy = DeviceArray(pol.value, (n_local,), "<i4", self)
+        self.d_terminal_mask = DeviceArray(term.value, (n_local,), "|u1", self)
+
+    def set_values(self, mask: np.ndarray, value: float) -> None:
+        """V[mask] = value on both buffers (the crane's goal initialisation,
+        runners/overhead_crane_cuda.py:193-206)."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        _ffi.check(_ffi.lib().pi_set_values(self._engine, _ffi.ptr(m), float(value)))
+
+    def build_table(self) -> None:
+        """Transition-table build (new stage; runs once, before the first sweep)."""
+        if not self._table_ready:
+            _ffi.check(_ffi.lib().pi_build_table(self._engine))
+            self._table_ready = True
+
+    # ── Policy iteration (:300-370) ───────────────────────────────────────────
+
+    def policy_evaluation(self) -> float:
+        """Iterative policy evaluation until convergence; returns the last residual."""
+        self.build_table()
+        delta, sweeps = C.c_float(), C.c_int32()
+        _ffi.check(_ffi.lib().pi_evaluate(self._engine, C.byref(delta), C.byref(sweeps)))
+        self.last_eval_sweeps = int(sweeps.value)
+        self._refresh_device_handles()
+        return float(delta.value)
+
+    def policy_improvement(self) -> bool:
+        """Greedy improvement; True if the policy is stable."""
+        self.build_table()
+        stable, changed = C.c_int32(), C.c_int64()
+        _ffi.check(_ffi.lib().pi_improve(self._engine, C.byref(stable), C.byref(changed)))
+        self.last_changed = int(changed.value)
+        return bool(stable.value)
+
+    def run(self) -> None:
+        """The complete policy-iteration loop (same for/else semantics as :357-370)."""
+        self.total_eval_sweeps = 0
+        self.pi_iterations = 0
+        for n in range(self.config.max_pi_iter):
+            logger.info(f"-- PI Iteration {n + 1}/{self.config.max_pi_iter} --")
+            self.policy_evaluation()
+            self.total_eval_sweeps += self.last_eval_sweeps
+            self.pi_iterations = n + 1
+            if self.policy_improvement():
+                logger.success(f"Policy Iteration converged at iteration {n + 1}.")
+                break
+        else:
+            logger.warning(f"Policy Iteration hit max_pi_iter={self.config.max_pi_iter}.")
+        self._pull_tensors_from_gpu()
+
+    def engine_stats(self) -> dict:
+        st = _ffi.PiStats()
+        _ffi.check(_ffi.lib().pi_get_stats(self._engine, C.byref(st)))
+        d = st.as_dict()
+        d["launches"] = int(_ffi.lib().pi_launch_count(self._engine))
+        d["table_bytes"] = int(_ffi.lib().pi_table_bytes(self._engine))
+        return d
+
+    def _pull_tensors_from_gpu(self) -> None:
+        """D2H of V and policy, then release VRAM (:372-388)."""
+        logger.info("Pulling results from VRAM to RAM...")
+        self.value_function = np.empty(self.n_states, dtype=np.float32)
+        self.policy = np.empty(self.n_states, dtype=np.int32)
+        _ffi.check(_ffi.lib().pi_copy_results(self._engine, _ffi.ptr(self.value_function), _ffi.ptr(self.policy)))
+        self.stats = self.engine_stats()
+        self.close()
+        logger.success("VRAM released. Results in CPU RAM.")
+
+    def close(self) -> None:
+        if getattr(self, "_engine", None):
+            _ffi.lib().pi_destroy(self._engine)
+            self._engine = None
+            for attr in ("d_value_function", "d_new_value_function", "d_policy", "d_terminal_mask"):
+                if hasattr(self, attr):
+                    delattr(self, attr)
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ── Persistence: the reference's nine-array .npz (:392-432) ───────────────
+
+    def save(self, filepath: Path | str) -> None:
+        filepath = Path(filepath).with_suffix(".npz")
+        filepath.parent.mkdir(parents=True, exist_ok=True)
+        np.savez(
+            filepath,
+            value_function=self.value_function,
+            policy=self.policy,
+            bounds_low=self.bounds_low,
+            bounds_high=self.bounds_high,
+            grid_shape=self.grid_shape,
+            strides=self.strides,
+            corner_bits=self.corner_bits,
+            action_space=self.action_space,
+            states_space=self.states_space,
+        )
+        logger.success(f"Policy saved to {filepath.resolve()}")
+
+    @classmethod
+    def load(cls, filepath: Path | str):
+        """Load a saved policy (no GPU required)."""
+        filepath = Path(filepath).with_suffix(".npz")
+        data = np.load(filepath)
+        instance = cls.__new__(cls)
+        instance._engine = None
+        instance._states_space = None
+        instance.value_function = data["value_function"]
+        instance.policy = data["policy"]
+        instance.bounds_low = data["bounds_low"]
+        instance.bounds_high = data["bounds_high"]
+        instance.grid_shape = data["grid_shape"]
+        instance.strides = data["strides"]
+        instance.corner_bits = data["corner_bits"]
+        instance.action_space = data["action_space"]
+        instance.states_space = data["states_space"]
+        instance.n_actions = len(instance.action_space)
+        instance.n_states = len(instance.states_space)
+        instance.config = CudaPIConfig()
+        logger.success(f"Policy loaded from {filepath.resolve()}")
+        return instance
+
+    # ── Extras beyond the reference surface (tests / bench / e2e call) ─────────
+
+    def upload_policy(self, policy: np.ndarray) -> None:
+        self.build_table()
+        p = np.ascontiguousarray(policy, dtype=np.int32)
+        assert p.shape == (self.n_states,)
+        _ffi.check(_ffi.lib().pi_upload_policy(self._engine, _ffi.ptr(p)))
+
+    def upload_values(self, values: np.ndarray) -> None:
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        assert v.shape == (self.n_states,)
+        _ffi.check(_ffi.lib().pi_upload_values(self._engine, _ffi.ptr(v)))
+
+    def download(self, values: np.ndarray | None = None, policy: np.ndarray | None = None):
+        if values is None:
+            values = np.empty(self.n_states, dtype=np.float32)
+        if policy is None:
+            policy = np.empty(self.n_states, dtype=np.int32)
+        _ffi.check(_ffi.lib().pi_copy_results(self._engine, _ffi.ptr(values), _ffi.ptr(policy)))
+        return values, policy
+
+    def sweeps(self, n: int) -> tuple[float, float]:
+        """Exactly n evaluation sweeps, no convergence test -> (last residual, device ms)."""
+        self.build_table()
+        delta, ms = C.c_float(), C.c_float()
+        _ffi.check(_ffi.lib().pi_sweeps(self._engine, int(n), C.byref(delta), C.byref(ms)))
+        self._refresh_device_handles()
+        return float(delta.value), float(ms.value)
+
+    def expand_rows(self, action: int, s_begin: int = 0, count: int | None = None):
+        """(idx, w, reward, terminated) in the reference's corner form, for parity checks."""
+        self.build_table()
+        lib = _ffi.lib()
+        if count is None:
+            count = lib.pi_local_end(self._engine) - s_begin
+        Cn = 1 << self.N_DIMS
+        idx = np.empty((count, Cn), dtype=np.int32)
+        w = np.empty((count, Cn), dtype=np.float32)
+        r = np.empty(count, dtype=np.float32)
+        t = np.empty(count, dtype=np.uint8)
+        _ffi.check(lib.pi_expand_rows(self._engine, int(action), int(s_begin), int(count), _ffi.ptr(idx), _ffi.ptr(w),
+                                      _ffi.ptr(r), _ffi.ptr(t)))
+        return idx, w, r, t
+
+
+class CudaPolicyIteration2D(_CudaPolicyIterationBase):
+    """Drop-in for the reference's CudaPolicyIteration2D (src/cuda_policy_iteration.py:46)."""
+    N_DIMS = 2
+
+
+class CudaPolicyIteration4D(_CudaPolicyIterationBase):
+    """Drop-in for the reference's CudaPolicyIteration4D (src/cuda_policy_iteration.py:439)."""
+    N_DIMS = 4
+
+
+class CudaPolicyIteration6D(_CudaPolicyIterationBase):
+    """Drop-in for the reference's CudaPolicyIteration6D (src/cuda_policy_iteration.py:847)."""
+    N_DIMS = 6

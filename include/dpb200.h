@@ -1,0 +1,194 @@
+/*
+ * dpb200.h — C ABI of the B200-native policy-iteration engine (libdpb200.so).
+ *
+ * This is the drop-in boundary for the hot path of
+ * nicoRomeroCuruchet/DynamicProgramming, src/cuda_policy_iteration.py.  The
+ * reference has no FFI of its own (its plugin boundary is a Python ABC plus a
+ * CUDA source string handed to cupy.RawModule); every entry point below cites
+ * the reference method (file:line, relative to the reference root) it replaces.
+ * A Python host binds these with ctypes (dynamicprogramming_b200/_ffi.py);
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status: PI_OK (0) or a PI_ERR_* class;
+ *     pi_last_error() returns a thread-local message (incl. the NVRTC log).
+ *   - plain pointers and sizes only; host buffers are caller-owned; the engine
+ *     owns all device memory, its stream, graphs and (multi-GPU) communicator.
+ *   - one caller thread per engine handle (same as the reference object).
+ *   - there is NO CPU fallback: without a CUDA device pi_create fails.
+ */
+#ifndef DPB200_H
+#define DPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PI_MAX_DIMS 6
+#define PI_ABI_VERSION 1
+
+enum {
+    PI_OK = 0,
+    PI_ERR_INVALID = 1,   /* bad argument / wrong call order              */
+    PI_ERR_CUDA = 2,      /* CUDA runtime / driver failure                */
+    PI_ERR_COMPILE = 3,   /* NVRTC rejected the dynamics source           */
+    PI_ERR_COMM = 4,      /* NCCL failure                                 */
+    PI_ERR_NO_DEVICE = 5  /* no usable CUDA device                        */
+};
+
+/* Row sentinels stored in the base-index word of a transition row. */
+#define PI_ROW_TERMINATED (-1) /* step_dynamics set *terminated: sum w*V := 0   */
+#define PI_ROW_ABSORBING (-2)  /* state is in the terminal mask: new_V := V     */
+
+typedef struct pi_engine pi_engine;
+
+/* Regular grid. Replaces bins_space + _precompute_grid_metadata
+ * (src/cuda_policy_iteration.py:81-109, :480-514, :894-937): dim 0 is the
+ * slowest, dim n_dims-1 has stride 1; lo/hi are the float32 min/max of each
+ * axis; axes[d] points to shape[d] float32 node coordinates (bit-identical to
+ * the columns of the reference's states_space). */
+typedef struct pi_grid {
+    int32_t n_dims;
+    int32_t shape[PI_MAX_DIMS];
+    float lo[PI_MAX_DIMS];
+    float hi[PI_MAX_DIMS];
+    const float* axes[PI_MAX_DIMS];
+} pi_grid;
+
+/* Mirrors CudaPIConfig (src/cuda_policy_iteration.py:36-43) plus the
+ * hard-coded SYNC_INTERVAL = 25 of policy_evaluation (:303). */
+typedef struct pi_config {
+    float gamma;
+    float theta;
+    int32_t max_eval_iter;
+    int32_t max_pi_iter;
+    int32_t log_interval;
+    int32_t sync_interval; /* 0 -> 25 */
+} pi_config;
+
+/* State-range sharding over the GPUs of one box (new; the reference is
+ * single-GPU).  Rank r owns flat states [r*N/world, (r+1)*N/world). */
+typedef struct pi_shard {
+    int32_t rank;
+    int32_t world_size;
+    uint8_t nccl_id[128]; /* ncclUniqueId bytes from rank 0; ignored if world_size==1 */
+} pi_shard;
+
+typedef struct pi_stats {
+    int32_t pi_iterations;    /* outer iterations executed                      */
+    int32_t converged;        /* 1 if the policy became stable                  */
+    int64_t eval_sweeps;      /* total evaluation sweeps                        */
+    float last_delta;         /* last residual read at a sync point             */
+    int64_t last_changed;     /* states whose action changed in the last improve*/
+    double build_ms;          /* device time of the transition-table build      */
+    double eval_ms;           /* device time inside evaluation sweeps           */
+    double improve_ms;        /* device time inside improvement passes          */
+} pi_stats;
+
+/* Log callback: level 0=debug 1=info 2=success 3=warning (loguru levels used
+ * by the reference, src/cuda_policy_iteration.py:106,:328-335,:360-368). */
+typedef void (*pi_log_fn)(int level, const char* msg, void* user);
+
+const char* pi_last_error(void);
+int pi_abi_version(void);
+
+/* Number of visible CUDA devices (0 when there is no driver). */
+int pi_device_count(void);
+
+/* Compile-only check of a plugin's dynamics source against the table-builder
+ * template (NVRTC, sm_100a); needs no GPU.  Errors carry the NVRTC log — the
+ * analogue of cupy's CompileException at src/cuda_policy_iteration.py:289. */
+int pi_compile_check(const char* dynamics_src, int32_t n_dims, int64_t* cubin_bytes);
+
+/* ncclGetUniqueId for pi_shard.nccl_id: rank 0 calls it and ships the 128 bytes
+ * to the other ranks through its own process group (torch.distributed). */
+int pi_nccl_unique_id(uint8_t out[128]);
+
+/* __init__ + _allocate_tensors_and_compile (src/cuda_policy_iteration.py:65-91,
+ * :142-175, :288-296).  `dynamics_src` is the string returned by the plugin's
+ * _dynamics_cuda_src() (:113-125, :518-530, :941-954); it is compiled by NVRTC
+ * (default options, like cupy.RawModule) into the transition-table builder.
+ * policy := 0, V := 0.  `shard` may be NULL (single GPU). */
+int pi_create(const pi_grid* grid, const float* actions, int32_t n_actions,
+              const pi_config* config, const char* dynamics_src, int32_t device,
+              const pi_shard* shard, pi_engine** out);
+
+void pi_destroy(pi_engine* e);
+
+int pi_set_log(pi_engine* e, pi_log_fn fn, void* user);
+
+/* Terminal mask + initial value: d_terminal_mask, V[mask] = value, new_V = V
+ * (src/cuda_policy_iteration.py:156-161).  `mask` has n_states bytes (global). */
+int pi_set_terminal(pi_engine* e, const uint8_t* mask, float value);
+
+/* V[mask] = value on both buffers without touching the terminal mask — the
+ * overhead-crane goal initialisation (runners/overhead_crane_cuda.py:193-206). */
+int pi_set_values(pi_engine* e, const uint8_t* mask, float value);
+
+/* Transition-table build (new stage; arithmetic oracle = step_dynamics +
+ * get_barycentric_{2,4,6}d, src/cuda_policy_iteration.py:183-210, :580-614,
+ * :1007-1042).  One compact row per (state, action): base flat index,
+ * n_dims interpolation fractions, reward.  Must follow pi_set_terminal. */
+int pi_build_table(pi_engine* e);
+
+/* policy_evaluation() (src/cuda_policy_iteration.py:300-336): Jacobi sweeps,
+ * residual read every sync_interval sweeps, returns at the first sync sweep
+ * with delta < theta.  *delta = value the reference would return; *sweeps =
+ * number of sweeps executed. */
+int pi_evaluate(pi_engine* e, float* delta, int32_t* sweeps);
+
+/* policy_improvement() (src/cuda_policy_iteration.py:338-355): greedy argmax,
+ * strict '>' from -1e30f so the lowest action index wins ties; *stable = 1 iff
+ * no state changed its action. */
+int pi_improve(pi_engine* e, int32_t* stable, int64_t* n_changed);
+
+/* run() (src/cuda_policy_iteration.py:357-370) without the final D2H. */
+int pi_run(pi_engine* e, pi_stats* stats);
+
+/* _pull_tensors_from_gpu (src/cuda_policy_iteration.py:372-388): global V and
+ * policy (n_states each) to host.  Multi-GPU: collective, every rank gets all. */
+int pi_copy_results(pi_engine* e, float* value_function, int32_t* policy);
+
+/* Host <-> device hand-off used by the end-to-end evaluation call and tests. */
+int pi_upload_policy(pi_engine* e, const int32_t* policy);     /* n_states  */
+int pi_upload_values(pi_engine* e, const float* value_function); /* n_states */
+
+/* Exactly `n_sweeps` evaluation sweeps with no convergence test (steady-state
+ * timing); *delta = residual of the last sweep, *device_ms = CUDA-event time. */
+int pi_sweeps(pi_engine* e, int32_t n_sweeps, float* delta, float* device_ms);
+
+/* Expand compact rows into the reference's 2^D corner form for parity checks:
+ * for `count` states starting at global state `s_begin` (must lie in this
+ * rank's range) and action `action`, writes idx[count][C], w[count][C],
+ * reward[count], terminated[count] exactly as step_dynamics +
+ * get_barycentric_Nd would produce them (corner c, bit d <-> dim d for
+ * D=4,6; the 2-D corner order of :201-209 for D=2).  Any output may be NULL. */
+int pi_expand_rows(pi_engine* e, int32_t action, int64_t s_begin, int64_t count,
+                   int32_t* idx, float* w, float* reward, uint8_t* terminated);
+
+/* Raw device pointers for torch/__cuda_array_interface__ hand-off
+ * (d_value_function, d_policy, ... of the reference object). */
+int pi_device_ptrs(pi_engine* e, void** value_function, void** new_value_function,
+                   void** policy, void** terminal_mask);
+
+/* Geometry queries. */
+int64_t pi_n_states(const pi_engine* e);
+int64_t pi_local_begin(const pi_engine* e);
+int64_t pi_local_end(const pi_engine* e);
+int64_t pi_table_bytes(const pi_engine* e);
+/* Number of kernel launches issued by this engine so far (bench bookkeeping). */
+int64_t pi_launch_count(const pi_engine* e);
+/* Last-stage device timings in ms (build, eval, improve). */
+int pi_get_stats(const pi_engine* e, pi_stats* stats);
+
+/* N2 (next row): batched policy lookup with get_optimal_action semantics
+ * (utils/barycentric.py:11-108; float64 arithmetic, corner_bits order).
+ * points: n_points x n_dims float32 (host); out: n_points float32 (host). */
+int pi_lookup_actions(pi_engine* e, const float* points, int64_t n_points, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPB200_H */
