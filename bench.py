@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""
+bench.py — policy-evaluation throughput (Bellman state-backups/s) on the
+reference's largest configuration: Double CartPole swing-up, 6-D, --bins 20
+(64 M states, 9 actions; BASELINE.json configs[4]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one sync interval of the reference's policy_evaluation loop
+(src/cuda_policy_iteration.py:300-336): 25 Jacobi sweeps over the whole grid
+under the policy produced by the first improvement pass.  Timed with CUDA
+events on the engine's stream (max over ranks).  Rank 0 prints ONE JSON line.
+
+  value        whole-job state-backups/s with the transition rows and V resident in HBM
+  e2e          the same through the public Python API with HOST buffers: every
+               step uploads the policy (pinned host -> device), re-compacts the
+               rows, runs the 25 sweeps and downloads V + the residual
+  roofline     HBM roofline of the evaluation-sweep kernel (algorithmic bytes =
+               compact row + V read + V write per backup)
+  cpu_baseline the CPU restatement (oracle/pi_oracle.c, OpenMP) on a bounded slab
+  --impl reference   the reference's OWN kernels (oracle/_ref cubins compiled from
+               /root/reference by NVRTC) driven by the reference's host loop on one
+               B200 — the reference has no CPU policy-iteration path
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ENV = "double_cartpole_swingup"
+SWEEPS_PER_STEP = 25
+METRIC = "bellman_state_backups_per_s"
+UNIT = "backups/s"
+
+
+def _quiet_logs() -> None:
+    try:
+        from loguru import logger
+
+        logger.remove()
+        logger.add(sys.stderr, level="WARNING")
+    except ImportError:
+        pass
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self) -> None:
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(bins: int) -> float | None:
+    """dram bytes per evaluation-sweep launch from the committed ncu summary (profiles/)."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(f"{ENV}@{bins}", {}).get("eval_sweep_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------- ours
+def run_ours(args) -> dict:
+    import torch
+
+    from dynamicprogramming_b200 import _ffi, dist as pdist, envs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    shard = pdist.make_shard(local) if world > 1 else None
+    td = pdist.init_process_group() if world > 1 else None
+
+    spec = envs.REGISTRY[ENV]
+    eng = spec.make(bins=args.bins, device=local, shard=shard)
+    N = eng.n_states
+    lib = _ffi.lib()
+    lo, hi = lib.pi_local_begin(eng._engine), lib.pi_local_end(eng._engine)
+    eng.build_table()
+    # policy of PI iteration 1: a bounded evaluation of the initial policy, then one improvement
+    eng.sweeps(2 * SWEEPS_PER_STEP)
+    eng.policy_improvement()
+    build_ms = eng.engine_stats()["build_ms"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if td is not None:
+            td.barrier()
+
+    # ---- device-resident arm -------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        eng.sweeps(SWEEPS_PER_STEP)
+    sampler = ClockSampler(local)
+    launches0 = lib.pi_launch_count(eng._engine)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        _, ms = eng.sweeps(SWEEPS_PER_STEP)
+        dev_ms += ms
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.pi_launch_count(eng._engine) - launches0
+    if td is not None:
+        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = N * SWEEPS_PER_STEP / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, host buffers out ---------------------
+    n_local = hi - lo
+    pol_host = torch.empty(N, dtype=torch.int32).pin_memory()
+    v_host = torch.empty(n_local, dtype=torch.float32).pin_memory()
+    _, p0 = eng.download()
+    pol_host.numpy()[:] = p0
+    pol_np, v_np = pol_host.numpy(), v_host.numpy()
+
+    def e2e_step():
+        _ffi.check(lib.pi_upload_policy(eng._engine, _ffi.ptr(pol_np)))         # H2D policy slice + row compaction
+        d, _ = eng.sweeps(SWEEPS_PER_STEP)
+        _ffi.check(lib.pi_copy_local_results(eng._engine, _ffi.ptr(v_np), None))  # D2H value slice
+        return d
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if td is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = N * SWEEPS_PER_STEP * args.steps / e2e_s
+
+    out = None
+    if rank == 0:
+        D = eng.N_DIMS
+        bytes_per_backup = (D + 2) * 4 + 4 + 4          # compact row + V read + V write
+        peak, peak_src = measured_peak()
+        per_gpu_backups = value / world
+        achieved = per_gpu_backups * bytes_per_backup / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{ENV} 6-D --bins {args.bins} ({N:,} states x {eng.n_actions} actions), "
+                                   f"policy evaluation, step = {SWEEPS_PER_STEP} Jacobi sweeps (one reference sync interval)",
+                       "policy": "greedy policy after PI iteration 1", "gamma": eng.config.gamma,
+                       "sharding": "contiguous state ranges, needs-driven V exchange (NCCL)" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (rows %.2f GB + V %.2f GB per sweep)" % (
+                           (D + 2) * 4 * N / 1e9, 4 * N / 1e9)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 4),
+                    "d2h_bytes_per_step": int(n_local * 4 + 4),
+                    "call": "pi_upload_policy + pi_sweeps(25) + pi_copy_local_results (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.bins), "kernel": f"pi::eval_sweep_kernel<{D}>",
+                         "peak_source": peak_src, "layout": "compact row (base + D fractions + reward)",
+                         "algorithmic_bytes_per_backup": bytes_per_backup,
+                         "survey_gather_counted_bytes_per_backup": (D + 2) * 4 + 4 * (1 << D) + 13,
+                         "per_gpu": world > 1},
+            "table_build": {"ms": build_ms, "rows_per_s": (hi - lo) * eng.n_actions / (build_ms * 1e-3),
+                            "bytes": int(lib.pi_table_bytes(eng._engine))},
+            "wall_s_timed_region": wall_s,
+        }
+    eng.close()
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args.bins)
+        if not args.no_converge and world == 1:
+            out["time_to_converge"] = time_to_converge()
+    if td is not None:
+        td.barrier()
+        td.destroy_process_group()
+    return out
+
+
+def cpu_baseline(bins: int, budget_s: float = 12.0) -> dict:
+    """CPU restatement (oracle port) on the first two dim-0 slabs of the same grid."""
+    from dynamicprogramming_b200 import envs
+    from oracle import cpu_oracle
+
+    spec = envs.REGISTRY[ENV]
+    axes = [np.asarray(v, np.float32) for v in spec.bins_space(bins).values()]
+    slabs = 2
+    sub = [axes[0][:slabs]] + axes[1:]
+    cfg = spec.config()
+    o = cpu_oracle.CpuPolicyIteration(ENV, sub, spec.actions, cfg.gamma, cfg.theta, 10, 1)
+    D = len(axes)
+    st = 1
+    for d in range(D - 1, -1, -1):
+        o.grid.shape[d] = bins
+        o.grid.strides[d] = st
+        o.grid.lo[d] = float(axes[d][0])
+        o.grid.hi[d] = float(axes[d][-1])
+        st *= bins
+    V = np.zeros(bins ** D, np.float32)
+    o.policy[:] = np.random.default_rng(0).integers(0, len(spec.actions), o.n_states).astype(np.int32)
+    o.eval_sweep(V)  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        o.eval_sweep(V)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 8:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": o.n_states * n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} sweeps over the first {slabs} of {bins} dim-0 slabs ({o.n_states:,} of {bins ** D:,} states), "
+                      f"oracle/pi_oracle.c with OpenMP on all host cores"}
+
+
+def time_to_converge() -> dict:
+    """Config K1 (Pendulum --bins 200) run to the end through the public API."""
+    from dynamicprogramming_b200 import envs
+
+    eng = envs.make("pendulum")
+    t0 = time.perf_counter()
+    eng.run()
+    dt = time.perf_counter() - t0
+    return {"workload": "pendulum 2-D --bins 200 (40,000 states x 21 actions), run() incl. table build and D2H",
+            "seconds": dt, "pi_iterations": eng.pi_iterations, "eval_sweeps": eng.total_eval_sweeps,
+            "eval_ms": eng.stats["eval_ms"], "improve_ms": eng.stats["improve_ms"]}
+
+
+# ---------------------------------------------------------------------- reference
+def run_reference(args) -> dict | None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    import torch
+
+    from dynamicprogramming_b200 import envs
+    from oracle import ref_runner
+
+    spec = envs.REGISTRY[ENV]
+    N = args.bins ** 6
+    cfg_desc = {"workload": f"{ENV} 6-D --bins {args.bins} ({N:,} states x {len(spec.actions)} actions), "
+                            f"policy evaluation, step = {SWEEPS_PER_STEP} Jacobi sweeps (one reference sync interval)"}
+    if ref_runner.available(ENV) and torch.cuda.is_available():
+        torch.cuda.set_device(0)
+        ref = ref_runner.from_engine_env(ENV, bins=args.bins)
+        # same policy protocol as our arm: bounded evaluation, one improvement
+        for _ in range(2 * SWEEPS_PER_STEP):
+            ref.eval_launch()
+            ref.d_value_function, ref.d_new_value_function = ref.d_new_value_function, ref.d_value_function
+        ref.improve_launch()
+
+        def step():
+            # policy_evaluation inner loop (:305-326): eval kernel + max|x-y| each sweep, one .get() per 25
+            for i in range(SWEEPS_PER_STEP):
+                ref.eval_launch()
+                d = ref._max_abs_diff()
+                ref.d_value_function, ref.d_new_value_function = ref.d_new_value_function, ref.d_value_function
+            return float(d.item())
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_per_step = e0.elapsed_time(e1) / args.steps
+        value = N * SWEEPS_PER_STEP / (ms_per_step * 1e-3)
+        kind = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                "sample": "the reference's own eval kernel + max|x-y| reduction (oracle/_ref cubin, NVRTC-compiled "
+                          "from /root/reference) on one B200, full grid; the reference has no CPU path"}
+    else:
+        cb = cpu_baseline(args.bins, budget_s=30.0)
+        value = cb["value"]
+        ms_per_step = N * SWEEPS_PER_STEP / value * 1e3
+        kind = dict(cb)
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc, "cpu_baseline": kind,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bins", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-converge", action="store_true")
+    args = ap.parse_args()
+    _quiet_logs()
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -88,6 +88,7 @@ SIGNATURES = {
     "pi_improve": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "pi_run": (C.c_int, [C.c_void_p, C.POINTER(PiStats)]),
     "pi_copy_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pi_copy_local_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pi_upload_policy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pi_upload_values": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pi_sweeps": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

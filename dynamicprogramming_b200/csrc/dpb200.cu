@@ -122,6 +122,7 @@ struct pi_engine {
     float* d_axes[PI_MAX_DIMS] = {};
     pi::Ctl* d_ctl = nullptr;
     pi::Ctl* h_ctl = nullptr;  // pinned, 4 slots
+    float* d_partial = nullptr;  // per-block residual maxima / change counts
     float* d_delta_g = nullptr;  // global residual after all-reduce (sharded)
     unsigned long long* d_changed_g = nullptr;
 
@@ -212,8 +213,11 @@ int compile_builder(pi_engine* e, const char* dynamics_src) {
 
 // -------------------------------------------------------------- dispatch ---
 template <int D>
-void launch_eval(pi_engine* e) {
+void launch_eval(pi_engine* e, int j, int check) {
     pi::EvalParams p{};
+    p.partial = e->d_partial;
+    p.j = j;
+    p.check = check;
     p.rows = e->d_rows;
     p.V0 = e->d_V[0];
     p.V1 = e->d_V[1];
@@ -232,7 +236,7 @@ void launch_improve(pi_engine* e) {
     p.rows = e->d_rows;
     p.V = e->d_V[e->cur];
     p.policy = e->d_policy;
-    p.ctl = e->d_ctl;
+    p.partial = reinterpret_cast<unsigned int*>(e->d_partial);
     p.n_local = e->n_local;
     p.n_pad = e->n_pad;
     p.n_actions = e->A;
@@ -283,35 +287,42 @@ int exchange_values(pi_engine* e, float* V) {
     return PI_OK;
 }
 
-// One batch = k sweeps (+ exchange each) [+ residual all-reduce + decide].
-int enqueue_batch_raw(pi_engine* e, int k, int parity, bool decide) {
+// One batch = k sweeps (+ exchange each) + one bookkeeping kernel.
+//   kBatchDecide : last sweep is a sync point -> reduce residual [+ all-reduce] + decide
+//   kBatchPlain  : no residual at all, only the sweep counter advances
+//   kBatchMeasure: residual of the last sweep is reduced but no convergence decision
+enum { kBatchDecide = 0, kBatchPlain = 1, kBatchMeasure = 2 };
+
+int enqueue_batch_raw(pi_engine* e, int k, int parity, int mode) {
+    const int has_check = mode != kBatchPlain;
     for (int i = 0; i < k; ++i) {
-        DISPATCH_D(e, launch_eval, e);
+        DISPATCH_D(e, launch_eval, e, i, (has_check && i == k - 1) ? 1 : 0);
         if (e->world > 1) {
             float* Vout = e->d_V[(parity + i + 1) & 1];
             int rc = exchange_values(e, Vout);
             if (rc) return rc;
         }
     }
-    if (decide) {
-        const float* src = &e->d_ctl->last_delta;
-        if (e->world > 1) {
-            NC(g_nccl.AllReduce(&e->d_ctl->last_delta, e->d_delta_g, 1, ncclFloat32, ncclMax, e->comm, e->stream));
-            src = e->d_delta_g;
-        }
-        pi::eval_decide_kernel<<<1, 1, 0, e->stream>>>(e->d_ctl, src, e->cfg.theta);
+    const int nb = (int)nblocks(e->n_local);
+    const bool fused = (mode == kBatchDecide && e->world == 1);
+    pi::eval_reduce_kernel<<<1, 1024, 0, e->stream>>>(e->d_ctl, e->d_partial, nb, k, has_check, fused ? 1 : 0,
+                                                       e->cfg.theta);
+    if (mode == kBatchDecide && e->world > 1) {
+        NC(g_nccl.AllReduce(&e->d_ctl->last_delta, e->d_delta_g, 1, ncclFloat32, ncclMax, e->comm, e->stream));
+        pi::eval_decide_kernel<<<1, 1, 0, e->stream>>>(e->d_ctl, e->d_delta_g, e->cfg.theta);
     }
     return PI_OK;
 }
 
 int build_graphs(pi_engine* e) {
+    // [start parity][0: one sweep + decide, 1: sync sweeps + decide, 2: sync sweeps, counter only]
     for (int par = 0; par < 2; ++par) {
         for (int kind = 0; kind < 3; ++kind) {
             if (e->graphs[par][kind]) { cudaGraphExecDestroy(e->graphs[par][kind]); e->graphs[par][kind] = nullptr; }
             const int k = kind == 0 ? 1 : e->cfg.sync_interval;
             cudaGraph_t graph;
             CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = enqueue_batch_raw(e, k, par, kind != 2);
+            int rc = enqueue_batch_raw(e, k, par, kind == 2 ? kBatchPlain : kBatchDecide);
             cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
             if (rc) return rc;
             if (ce != cudaSuccess) return fail(PI_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -322,18 +333,20 @@ int build_graphs(pi_engine* e) {
     return PI_OK;
 }
 
-int enqueue_batch(pi_engine* e, int k, int parity, bool decide) {
+int enqueue_batch(pi_engine* e, int k, int parity, int mode) {
     const int sync = e->cfg.sync_interval;
-    if (k == 1 && decide && e->graphs[parity][0]) {
+    if (k == 1 && mode == kBatchDecide && e->graphs[parity][0]) {
         CU(cudaGraphLaunch(e->graphs[parity][0], e->stream));
-    } else if (k == sync && e->graphs[parity][decide ? 1 : 2]) {
-        CU(cudaGraphLaunch(e->graphs[parity][decide ? 1 : 2], e->stream));
+    } else if (k == sync && mode == kBatchDecide && e->graphs[parity][1]) {
+        CU(cudaGraphLaunch(e->graphs[parity][1], e->stream));
+    } else if (k == sync && mode == kBatchPlain && e->graphs[parity][2]) {
+        CU(cudaGraphLaunch(e->graphs[parity][2], e->stream));
     } else {
-        int rc = enqueue_batch_raw(e, k, parity, decide);
+        int rc = enqueue_batch_raw(e, k, parity, mode);
         if (rc) return rc;
         CU(cudaGetLastError());
     }
-    e->launches += k + (decide ? 1 : 0);
+    e->launches += k + 1;
     return PI_OK;
 }
 
@@ -444,6 +457,7 @@ int pi_create(const pi_grid* grid, const float* actions, int32_t n_actions, cons
     CUX(cudaMalloc(&e->d_rows, W * 4 * (size_t)e->n_pad));
     CUX(cudaMalloc(&e->d_actions, (size_t)e->A * 4));
     CUX(cudaMalloc(&e->d_ctl, sizeof(pi::Ctl)));
+    CUX(cudaMalloc(&e->d_partial, (size_t)nblocks(e->n_local) * 4 + 4));
     CUX(cudaMalloc(&e->d_delta_g, 4));
     CUX(cudaMalloc(&e->d_changed_g, 8));
     CUX(cudaMallocHost(&e->h_ctl, 4 * sizeof(pi::Ctl)));
@@ -481,7 +495,7 @@ void pi_destroy(pi_engine* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     cudaFree(e->d_V[0]); cudaFree(e->d_V[1]); cudaFree(e->d_policy); cudaFree(e->d_term);
     cudaFree(e->d_mask_full); cudaFree(e->d_table); cudaFree(e->d_rows); cudaFree(e->d_actions);
-    cudaFree(e->d_ctl); cudaFree(e->d_delta_g); cudaFree(e->d_changed_g);
+    cudaFree(e->d_ctl); cudaFree(e->d_partial); cudaFree(e->d_delta_g); cudaFree(e->d_changed_g);
     for (auto& a : e->d_axes) cudaFree(a);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -600,7 +614,7 @@ int pi_evaluate(pi_engine* e, float* delta_out, int32_t* sweeps_out) {
             int c = (enq % sync == 0) ? enq : (enq / sync + 1) * sync;  // next sync sweep index (:325)
             if (c > max_eval - 1) c = max_eval - 1;
             const int k = c - enq + 1;
-            int rc = enqueue_batch(e, k, (cur0 + enq) & 1, true);
+            int rc = enqueue_batch(e, k, (cur0 + enq) & 1, kBatchDecide);
             if (rc) return rc;
             const int slot = head & 3;
             CU(cudaMemcpyAsync(&e->h_ctl[slot], e->d_ctl, sizeof(pi::Ctl), cudaMemcpyDeviceToHost, e->stream));
@@ -629,13 +643,13 @@ int pi_evaluate(pi_engine* e, float* delta_out, int32_t* sweeps_out) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1));
     e->stats.eval_ms += ms;
-    e->cur = (cur0 + last.sweep) & 1;
-    e->stats.eval_sweeps += last.sweep;
+    e->cur = (cur0 + last.base) & 1;
+    e->stats.eval_sweeps += last.base;
     e->stats.last_delta = last.check_delta;
     if (!done)
         logf(e, 3, "  Eval hit max_eval_iter=%d | delta = %.2e", max_eval, (double)last.check_delta);
     if (delta_out) *delta_out = last.check_delta;
-    if (sweeps_out) *sweeps_out = last.sweep;
+    if (sweeps_out) *sweeps_out = last.base;
     e->results_gathered = false;
     return PI_OK;
 }
@@ -644,10 +658,11 @@ int pi_improve(pi_engine* e, int32_t* stable, int64_t* n_changed) {
     if (!e) return fail(PI_ERR_INVALID, "null engine");
     if (!e->table_built) return fail(PI_ERR_INVALID, "pi_build_table has not been called");
     CU(cudaSetDevice(e->device));
-    CU(cudaMemsetAsync(&e->d_ctl->changed, 0, 8, e->stream));
     CU(cudaEventRecord(e->ev_t0, e->stream));
     DISPATCH_D(e, launch_improve, e);
-    e->launches++;
+    pi::count_reduce_kernel<<<1, 1024, 0, e->stream>>>(e->d_ctl, reinterpret_cast<unsigned int*>(e->d_partial),
+                                                        (int)nblocks(e->n_local));
+    e->launches += 2;
     CU(cudaGetLastError());
     unsigned long long* src = &e->d_ctl->changed;
     if (e->world > 1) {
@@ -745,6 +760,17 @@ int pi_copy_results(pi_engine* e, float* value_function, int32_t* policy) {
     return PI_OK;
 }
 
+int pi_copy_local_results(pi_engine* e, float* v_local, int32_t* policy_local) {
+    if (!e) return fail(PI_ERR_INVALID, "null engine");
+    CU(cudaSetDevice(e->device));
+    if (v_local)
+        CU(cudaMemcpyAsync(v_local, e->d_V[e->cur] + e->s_begin, (size_t)e->n_local * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (policy_local)
+        CU(cudaMemcpyAsync(policy_local, e->d_policy, (size_t)e->n_local * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return PI_OK;
+}
+
 int pi_upload_policy(pi_engine* e, const int32_t* policy) {
     if (!e || !policy) return fail(PI_ERR_INVALID, "null argument");
     if (!e->table_built) return fail(PI_ERR_INVALID, "pi_build_table has not been called");
@@ -779,7 +805,7 @@ int pi_sweeps(pi_engine* e, int32_t n_sweeps, float* delta, float* device_ms) {
     int enq = 0;
     while (enq < n_sweeps) {
         const int k = std::min(sync, n_sweeps - enq);
-        int rc = enqueue_batch(e, k, (cur0 + enq) & 1, false);
+        int rc = enqueue_batch(e, k, (cur0 + enq) & 1, enq + k == n_sweeps ? kBatchMeasure : kBatchPlain);
         if (rc) return rc;
         enq += k;
     }

@@ -34,16 +34,14 @@ constexpr int kMaxDims = 6;
 // (src/cuda_policy_iteration.py:300-336).
 // ---------------------------------------------------------------------------
 struct Ctl {
-    unsigned int delta_bits;    // running max |new_V - V| of the sweep in flight (float bits, >= 0)
-    unsigned int ticket;        // blocks finished in the sweep in flight
-    int sweep;                  // sweeps completed since the evaluation started
+    int base;                   // sweeps completed before the batch in flight
     int parity0;                // V buffer that was "current" when the evaluation started
     int done;                   // 1 once a sync-point residual was < theta
     int conv_sweep;             // index i of the sweep at which the evaluation converged
-    float last_delta;           // residual of the last completed sweep (local to this rank)
+    float last_delta;           // residual of the last examined sweep (local to this rank)
     float check_delta;          // residual examined at the last sync point (global)
-    unsigned long long changed; // improvement: states whose action changed
-    unsigned int pad[6];
+    unsigned long long changed; // improvement: states whose action changed (local)
+    unsigned int pad[8];
 };
 
 struct GridDesc {
@@ -227,18 +225,21 @@ struct EvalParams {
     float* V0;                  // ping
     float* V1;                  // pong  (both full length n_states)
     Ctl* ctl;
+    float* partial;             // per-block residual maxima (written on check sweeps only)
     long long n_local;
     long long n_pad;
     long long s_begin;  // first global state of this rank
     float gamma;
+    int j;      // position of this launch inside its batch: sweep index = ctl->base + j
+    int check;  // 1 if the host will examine the residual of this sweep (sync point, :325)
     int stride[kMaxDims];
 };
 
 template <int D>
 __global__ void __launch_bounds__(kBlock) eval_sweep_kernel(const EvalParams p) {
-    Ctl* __restrict__ ctl = p.ctl;
-    if (*(volatile int*)&ctl->done) return;
-    const int par = (ctl->sweep + ctl->parity0) & 1;
+    const Ctl* __restrict__ ctl = p.ctl;
+    if (ctl->done) return;
+    const int par = (ctl->base + p.j + ctl->parity0) & 1;
     const float* __restrict__ Vin = par ? p.V1 : p.V0;
     float* __restrict__ Vout = par ? p.V0 : p.V1;
 
@@ -266,51 +267,63 @@ __global__ void __launch_bounds__(kBlock) eval_sweep_kernel(const EvalParams p) 
         Vout[p.s_begin + s] = vnew;
         res = fabsf(vnew - vold);
     }
+    if (!p.check) return;  // the reference reads the residual only at sync points (:325-326)
 
-    // block residual -> one atomicMax per block (non-negative floats order like unsigned ints)
+    // block residual -> partial[blockIdx]; reduced by eval_reduce_kernel (no atomics on the sweep path)
     __shared__ float s_red[kBlock / 32];
-    __shared__ bool s_last;
     res = warp_max(res);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = res;
     __syncthreads();
     if (threadIdx.x < 32) {
         float r = threadIdx.x < kBlock / 32 ? s_red[threadIdx.x] : 0.0f;
         r = warp_max(r);
-        if (threadIdx.x == 0) {
-            atomicMax(&ctl->delta_bits, __float_as_uint(r));
-            __threadfence();
-            const unsigned t = atomicAdd(&ctl->ticket, 1u);
-            s_last = (t == gridDim.x - 1);
-        }
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        const unsigned bits = atomicExch(&ctl->delta_bits, 0u);
-        ctl->last_delta = __uint_as_float(bits);
-        ctl->ticket = 0u;
-        ctl->sweep = ctl->sweep + 1;
-        __threadfence();
+        if (threadIdx.x == 0) p.partial[blockIdx.x] = r;
     }
 }
 
-// Sync point of policy_evaluation (:325-331): runs after the residual has been
-// made global (all-reduce when sharded).  `delta_src` is where the residual of
-// the sweep just completed lives.
+// End of a batch of k sweeps: advance the sweep counter; if the last sweep was a
+// check sweep, reduce the per-block residuals; if `decide`, apply the sync-point
+// test of policy_evaluation (:325-331).  When sharded the residual is all-reduced
+// between this kernel (decide = 0) and eval_decide_kernel.
+__global__ void __launch_bounds__(1024) eval_reduce_kernel(Ctl* ctl, const float* partial, int n_partial, int k,
+                                                          int has_check, int decide, float theta) {
+    if (ctl->done) return;
+    __shared__ float s_red[32];
+    float r = 0.0f;
+    if (has_check) {
+        for (int i = threadIdx.x; i < n_partial; i += blockDim.x) r = fmaxf(r, partial[i]);
+        r = warp_max(r);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = r;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            r = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.0f;
+            r = warp_max(r);
+        }
+    }
+    if (threadIdx.x == 0) {
+        ctl->base += k;
+        if (has_check) {
+            ctl->last_delta = r;
+            if (decide) {
+                ctl->check_delta = r;
+                if (r < theta) { ctl->done = 1; ctl->conv_sweep = ctl->base - 1; }
+            }
+        }
+    }
+}
+
 __global__ void eval_decide_kernel(Ctl* ctl, const float* delta_src, float theta) {
     if (ctl->done) return;
     const float d = *delta_src;
     ctl->check_delta = d;
     if (d < theta) {
         ctl->done = 1;
-        ctl->conv_sweep = ctl->sweep - 1;
+        ctl->conv_sweep = ctl->base - 1;
     }
 }
 
 __global__ void eval_begin_kernel(Ctl* ctl, int parity0) {
-    ctl->delta_bits = 0u;
-    ctl->ticket = 0u;
-    ctl->sweep = 0;
+    ctl->base = 0;
     ctl->parity0 = parity0;
     ctl->done = 0;
     ctl->conv_sweep = -1;
@@ -331,7 +344,7 @@ struct ImproveParams {
     unsigned char* rows;         // out: compacted rows of the new policy
     const float* V;              // current value function (full length)
     int* policy;                 // local policy (n_local)
-    Ctl* ctl;
+    unsigned int* partial;       // per-block count of states whose action changed
     long long n_local;
     long long n_pad;
     int n_actions;
@@ -387,7 +400,22 @@ __global__ void __launch_bounds__(kBlock) improve_kernel(const ImproveParams p) 
     __syncthreads();
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
     __syncthreads();
-    if (threadIdx.x == 0 && s_cnt) atomicAdd(&p.ctl->changed, (unsigned long long)s_cnt);
+    if (threadIdx.x == 0) p.partial[blockIdx.x] = (unsigned)s_cnt;
+}
+
+__global__ void __launch_bounds__(1024) count_reduce_kernel(Ctl* ctl, const unsigned int* partial, int n_partial) {
+    __shared__ unsigned long long s_red[32];
+    unsigned long long r = 0;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) r += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+        ctl->changed = t;
+    }
 }
 
 // rows[s] = table[policy[s]][s]  (after pi_upload_policy and at start-up)

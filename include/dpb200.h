@@ -151,6 +151,9 @@ int pi_run(pi_engine* e, pi_stats* stats);
  * policy (n_states each) to host.  Multi-GPU: collective, every rank gets all. */
 int pi_copy_results(pi_engine* e, float* value_function, int32_t* policy);
 
+/* This rank's slice only (states [pi_local_begin, pi_local_end)); no collective. */
+int pi_copy_local_results(pi_engine* e, float* value_function_local, int32_t* policy_local);
+
 /* Host <-> device hand-off used by the end-to-end evaluation call and tests. */
 int pi_upload_policy(pi_engine* e, const int32_t* policy);     /* n_states  */
 int pi_upload_values(pi_engine* e, const float* value_function); /* n_states */

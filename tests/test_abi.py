@@ -1,0 +1,100 @@
+"""C-ABI library: loads, exports every symbol include/dpb200.h declares, fails
+loudly without a device, compiles every plugin's dynamics (CPU only, no compute)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from dynamicprogramming_b200 import _ffi, envs
+from dynamicprogramming_b200.engine import CudaPIConfig
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared_functions() -> list[str]:
+    text = (ROOT / "include" / "dpb200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b(pi_[a-z_0-9]+)\s*\(", text)
+    return sorted(set(n for n in names if n not in ("pi_log_fn",)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _ffi.lib()
+    declared = _declared_functions()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dpb200.h but not exported"
+    # and the binding table covers the header (no stale / missing prototypes)
+    assert sorted(_ffi.SIGNATURES) == declared
+    assert lib.pi_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_ffi.PiConfig) == 24
+    assert C.sizeof(_ffi.PiShard) == 136
+    assert C.sizeof(_ffi.PiGrid) == 4 + 4 * 6 + 4 * 6 + 4 * 6 + 4 + 8 * 6  # incl. padding before the pointers
+    assert C.sizeof(_ffi.PiStats) == 56
+
+
+@pytest.mark.parametrize("name", sorted(envs.REGISTRY))
+def test_every_plugin_compiles_against_the_table_builder(name):
+    spec = envs.REGISTRY[name]
+    inst = spec.cls.__new__(spec.cls)
+    for k, v in spec.kwargs.items():
+        setattr(inst, k, v)
+    n = C.c_int64()
+    rc = _ffi.lib().pi_compile_check(inst._dynamics_cuda_src().encode(), spec.cls.N_DIMS, C.byref(n))
+    assert rc == 0, _ffi.lib().pi_last_error().decode()
+    assert n.value > 1000
+
+
+def test_compile_error_carries_the_nvrtc_log():
+    bad = "__device__ void step_dynamics(float a, float b, float u, float* x, float* y, float* r, bool* t) { oops; }"
+    rc = _ffi.lib().pi_compile_check(bad.encode(), 2, None)
+    assert rc == _ffi.PI_ERR_COMPILE
+    msg = _ffi.lib().pi_last_error().decode()
+    assert "oops" in msg and "error" in msg.lower()
+    with pytest.raises(_ffi.EngineError) as ei:
+        _ffi.check(rc)
+    assert ei.value.code == _ffi.PI_ERR_COMPILE
+
+
+def test_wrong_signature_is_a_compile_error():
+    # a 2-D plugin handed to a 4-D engine: the generated call does not match
+    src = envs.REGISTRY["pendulum"].cls.__new__(envs.REGISTRY["pendulum"].cls)._dynamics_cuda_src()
+    assert _ffi.lib().pi_compile_check(src.encode(), 4, None) == _ffi.PI_ERR_COMPILE
+
+
+def test_invalid_arguments():
+    lib = _ffi.lib()
+    assert lib.pi_compile_check(None, 2, None) == _ffi.PI_ERR_INVALID
+    assert lib.pi_compile_check(b"", 9, None) == _ffi.PI_ERR_INVALID
+    assert lib.pi_n_states(None) == 0
+    lib.pi_destroy(None)  # no-op
+
+
+def test_no_device_means_loud_failure_not_cpu_fallback():
+    lib = _ffi.lib()
+    if lib.pi_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_ffi.EngineError) as ei:
+        envs.make("pendulum", bins=8)
+    assert ei.value.code == _ffi.PI_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_wrong_number_of_dimensions_asserts_like_the_reference():
+    spec = envs.REGISTRY["pendulum"]
+    bins = {"a": np.linspace(0, 1, 4, dtype=np.float32)}
+    with pytest.raises(AssertionError):
+        spec.cls(bins, spec.actions, CudaPIConfig())
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure; the product path must not route through it."""
+    pkg = ROOT / "dynamicprogramming_b200"
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[/.](cpu_oracle|ref_runner|pi_oracle|_ref|_build)", re.M)
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")):
+        assert not pat.search(path.read_text()), f"{path} references oracle/"
