@@ -96,6 +96,7 @@ SIGNATURES = {
                                  C.c_void_p]),
     "pi_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_void_p)]),
+    "pi_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "pi_n_states": (C.c_int64, [C.c_void_p]),
     "pi_local_begin": (C.c_int64, [C.c_void_p]),
     "pi_local_end": (C.c_int64, [C.c_void_p]),

@@ -116,6 +116,14 @@ struct pi_engine {
     int* d_policy = nullptr;
     unsigned char* d_term = nullptr;       // local terminal mask
     unsigned char* d_mask_full = nullptr;  // scratch for set_terminal / set_values (N bytes)
+    void* d_scratch = nullptr;             // N*4 bytes, reference-order staging when the layout is permuted
+    int fast_dim = -1;                     // logical dimension stored with stride 1
+    bool identity_layout = true;
+    int sm_count = 148;
+    int blocks_per_sm = 4;                 // resident evaluation blocks per SM (occupancy query)
+    int lookahead = 0;                     // L2 row prefetch distance in blocks (DPB200_LOOKAHEAD, default = resident blocks)
+    bool pair_kernel = false;              // evaluation sweeps use eval_sweep_pair_kernel<D, fast_dim>
+    double probe_lines[PI_MAX_DIMS] = {};  // layout probe: avg 128-B lines per warp gather, per candidate
     unsigned char* d_table = nullptr;
     unsigned char* d_rows = nullptr;
     float* d_actions = nullptr;
@@ -211,13 +219,117 @@ int compile_builder(pi_engine* e, const char* dynamics_src) {
     return PI_OK;
 }
 
+// ------------------------------------------------------------ table build --
+void set_layout(pi_engine* e, int fast_dim) {
+    const int D = e->D;
+    int k = 0;
+    for (int d = 0; d < D; ++d)
+        if (d != fast_dim) e->g.perm[k++] = d;
+    e->g.perm[D - 1] = fast_dim;
+    long long st = 1;
+    for (int pos = D - 1; pos >= 0; --pos) {
+        e->g.istride[e->g.perm[pos]] = (int)st;
+        st *= e->g.shape[e->g.perm[pos]];
+    }
+    e->fast_dim = fast_dim;
+    e->identity_layout = (fast_dim == D - 1);
+}
+
+// Launch the NVRTC-compiled builder for `n_states` internal states starting at `s_begin`.
+int launch_build(pi_engine* e, unsigned char* table, const float* actions, int n_actions, const unsigned char* absorbing,
+                 long long n_states, long long n_pad, long long s_begin) {
+    // parameter block: natural alignment, arrays of PI_D entries — must match table_build_src.h
+    std::vector<unsigned char> b;
+    put(b, table, 8);
+    put(b, actions, 8);
+    put(b, absorbing, 8);
+    for (int d = 0; d < e->D; ++d) { const float* ax = e->d_axes[d]; put(b, ax, 8); }
+    put(b, n_states, 8);
+    put(b, n_pad, 8);
+    put(b, s_begin, 8);
+    put(b, n_actions, 4);
+    for (int d = 0; d < e->D; ++d) put(b, e->g.shape[d], 4);
+    for (int d = 0; d < e->D; ++d) put(b, e->g.istride[d], 4);
+    for (int d = 0; d < e->D; ++d) put(b, e->g.lo[d], 4);
+    for (int d = 0; d < e->D; ++d) put(b, e->g.hi[d], 4);
+    for (int d = 0; d < e->D; ++d) put(b, e->g.perm[d], 4);
+    while (b.size() % 8) b.push_back(0);
+    void* args[] = {b.data()};
+    dim3 grid(nblocks(n_states), (unsigned)n_actions, 1);
+    CU(cudaLaunchKernel((const void*)e->build_kernel, grid, dim3(pi::kBlock, 1, 1), args, 0, e->stream));
+    e->launches++;
+    return PI_OK;
+}
+
+// Layout probe: for every candidate fast dimension build the rows of the
+// middle action for a few sample chunks and count the 128-byte lines a warp's V gather
+// touches; keep the candidate with the fewest.  DPB200_FAST_DIM = ref | auto | <dim>.
+int choose_layout(pi_engine* e) {
+    const int D = e->D;
+    const char* env = getenv("DPB200_FAST_DIM");
+    if (env && (!strcmp(env, "ref") || !strcmp(env, "reference"))) { set_layout(e, D - 1); return PI_OK; }
+    if (env && env[0] >= '0' && env[0] <= '9') {
+        int f = atoi(env);
+        if (f < 0 || f >= D) return fail(PI_ERR_INVALID, "DPB200_FAST_DIM=%d out of range", f);
+        set_layout(e, f);
+        return PI_OK;
+    }
+    const long long chunk = std::min<long long>(e->N, 16384);
+    const int n_chunks = e->N > 8 * chunk ? 4 : 1;
+    const long long n_pad = (chunk + 31) / 32 * 32;
+    const size_t W = (size_t)D + 2;
+    unsigned char* tmp = nullptr;
+    unsigned long long* cnt = nullptr;
+    CU(cudaMalloc(&tmp, W * 4 * (size_t)n_pad));
+    CU(cudaMalloc(&cnt, 16));
+    const int first_plane = W >= 4 ? 16 : (W >= 2 ? 8 : 4);
+    int best = D - 1;
+    double best_lines = 1e30;
+    for (int f = D - 1; f >= 0; --f) {
+        set_layout(e, f);
+        CU(cudaMemsetAsync(cnt, 0, 16, e->stream));
+        for (int c = 0; c < n_chunks; ++c) {
+            const long long s0 = n_chunks == 1 ? 0 : (e->N / 8) * (2 * c + 1) / 32 * 32;
+            const long long n = std::min(chunk, e->N - s0);
+            int rc = launch_build(e, tmp, e->d_actions + e->A / 2, 1, nullptr, n, n_pad, s0);
+            if (rc) return rc;
+            pi::gather_lines_kernel<<<nblocks(n), pi::kBlock, 0, e->stream>>>(tmp, first_plane, n, cnt, cnt + 1);
+            e->launches++;
+        }
+        unsigned long long h[2];
+        CU(cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        const double lines = h[1] ? (double)h[0] / (double)h[1] : 32.0;
+        e->probe_lines[f] = lines;
+        if (lines < best_lines * 0.95) { best_lines = lines; best = f; }  // prefer the reference order on near-ties
+    }
+    cudaFree(tmp);
+    cudaFree(cnt);
+    set_layout(e, best);
+    return PI_OK;
+}
+
 // -------------------------------------------------------------- dispatch ---
+inline unsigned eval_blocks(const pi_engine* e) {
+    return e->pair_kernel ? nblocks((e->n_local + 1) / 2) : nblocks(e->n_local);
+}
+
+template <int D, int F>
+void launch_pair(pi_engine* e, const pi::EvalParams& p) {
+    if constexpr (F < D && pi::corner_pos<D>(F) <= 2)
+        pi::eval_sweep_pair_kernel<D, F><<<eval_blocks(e), pi::kBlock, 0, e->stream>>>(p);
+}
+
+template <int D>
+bool pair_supported(int fast_dim) { return fast_dim >= 0 && fast_dim < D && pi::corner_pos<D>(fast_dim) <= 2; }
+
 template <int D>
 void launch_eval(pi_engine* e, int j, int check) {
     pi::EvalParams p{};
     p.partial = e->d_partial;
     p.j = j;
     p.check = check;
+    p.lookahead = e->lookahead;
     p.rows = e->d_rows;
     p.V0 = e->d_V[0];
     p.V1 = e->d_V[1];
@@ -226,8 +338,27 @@ void launch_eval(pi_engine* e, int j, int check) {
     p.n_pad = e->n_pad;
     p.s_begin = e->s_begin;
     p.gamma = e->cfg.gamma;
-    for (int d = 0; d < D; ++d) p.stride[d] = e->g.stride[d];
-    pi::eval_sweep_kernel<D><<<nblocks(e->n_local), pi::kBlock, 0, e->stream>>>(p);
+    for (int d = 0; d < D; ++d) p.stride[d] = e->g.istride[d];
+    if (e->pair_kernel) {
+        switch (e->fast_dim) {
+            case 0: launch_pair<D, 0>(e, p); break;
+            case 1: launch_pair<D, 1>(e, p); break;
+            case 2: launch_pair<D, 2>(e, p); break;
+            case 3: launch_pair<D, 3>(e, p); break;
+            case 4: launch_pair<D, 4>(e, p); break;
+            case 5: launch_pair<D, 5>(e, p); break;
+            default: break;
+        }
+        return;
+    }
+    pi::eval_sweep_kernel<D><<<eval_blocks(e), pi::kBlock, 0, e->stream>>>(p);
+}
+template <int D>
+void query_pair_supported(pi_engine* e, bool* out) { *out = pair_supported<D>(e->fast_dim); }
+template <int D>
+void query_eval_occupancy(pi_engine* e, int* blocks) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pi::eval_sweep_kernel<D>, pi::kBlock, 0) != cudaSuccess)
+        *blocks = 2;
 }
 template <int D>
 void launch_improve(pi_engine* e) {
@@ -241,7 +372,7 @@ void launch_improve(pi_engine* e) {
     p.n_pad = e->n_pad;
     p.n_actions = e->A;
     p.gamma = e->cfg.gamma;
-    for (int d = 0; d < D; ++d) p.stride[d] = e->g.stride[d];
+    for (int d = 0; d < D; ++d) p.stride[d] = e->g.istride[d];
     pi::improve_kernel<D><<<nblocks(e->n_local), pi::kBlock, 0, e->stream>>>(p);
 }
 template <int D>
@@ -253,7 +384,8 @@ template <int D>
 void launch_expand(pi_engine* e, int action, long long s0, long long count, int* idx, float* w, float* rw,
                    unsigned char* tm) {
     const unsigned char* tab = e->d_table + (size_t)action * pi::row_table_bytes(D, e->n_pad);
-    pi::expand_rows_kernel<D><<<nblocks(count), pi::kBlock, 0, e->stream>>>(tab, e->n_pad, s0, count, e->g, idx, w, rw, tm);
+    pi::expand_rows_kernel<D><<<nblocks(count), pi::kBlock, 0, e->stream>>>(tab, e->n_pad, s0, count, e->g, e->s_begin,
+                                                                         e->n_local, idx, w, rw, tm);
 }
 
 #define DISPATCH_D(e, fn, ...)                                     \
@@ -303,7 +435,7 @@ int enqueue_batch_raw(pi_engine* e, int k, int parity, int mode) {
             if (rc) return rc;
         }
     }
-    const int nb = (int)nblocks(e->n_local);
+    const int nb = (int)eval_blocks(e);
     const bool fused = (mode == kBatchDecide && e->world == 1);
     pi::eval_reduce_kernel<<<1, 1024, 0, e->stream>>>(e->d_ctl, e->d_partial, nb, k, has_check, fused ? 1 : 0,
                                                        e->cfg.theta);
@@ -412,6 +544,7 @@ int pi_create(const pi_grid* grid, const float* actions, int32_t n_actions, cons
     if (e->cfg.sync_interval <= 0) e->cfg.sync_interval = 25;
     e->device = device;
     long long st = 1;
+    e->g.n_dims = e->D;
     for (int d = e->D - 1; d >= 0; --d) {
         e->g.shape[d] = grid->shape[d];
         e->g.stride[d] = (int)st;
@@ -419,6 +552,7 @@ int pi_create(const pi_grid* grid, const float* actions, int32_t n_actions, cons
         e->g.hi[d] = grid->hi[d];
         st *= grid->shape[d];
     }
+    set_layout(e, e->D - 1);
     if (shard && shard->world_size > 1) {
         e->rank = shard->rank;
         e->world = shard->world_size;
@@ -449,20 +583,21 @@ int pi_create(const pi_grid* grid, const float* actions, int32_t n_actions, cons
     if (rc) { pi_destroy(e); return rc; }
 
     const size_t W = (size_t)e->D + 2;
-    CUX(cudaMalloc(&e->d_V[0], (size_t)N * 4));
-    CUX(cudaMalloc(&e->d_V[1], (size_t)N * 4));
+    // +32 B: the pair kernel reads aligned 64-bit windows that may end one element past N-1
+    CUX(cudaMalloc(&e->d_V[0], (size_t)N * 4 + 32));
+    CUX(cudaMalloc(&e->d_V[1], (size_t)N * 4 + 32));
     CUX(cudaMalloc(&e->d_policy, (size_t)e->n_pad * 4));
     CUX(cudaMalloc(&e->d_term, (size_t)e->n_pad));
     CUX(cudaMalloc(&e->d_table, (size_t)e->A * W * 4 * (size_t)e->n_pad));
     CUX(cudaMalloc(&e->d_rows, W * 4 * (size_t)e->n_pad));
     CUX(cudaMalloc(&e->d_actions, (size_t)e->A * 4));
     CUX(cudaMalloc(&e->d_ctl, sizeof(pi::Ctl)));
-    CUX(cudaMalloc(&e->d_partial, (size_t)nblocks(e->n_local) * 4 + 4));
+    CUX(cudaMalloc(&e->d_partial, (size_t)nblocks(e->n_local) * 4 + 4));  // >= any grid used below
     CUX(cudaMalloc(&e->d_delta_g, 4));
     CUX(cudaMalloc(&e->d_changed_g, 8));
     CUX(cudaMallocHost(&e->h_ctl, 4 * sizeof(pi::Ctl)));
-    CUX(cudaMemsetAsync(e->d_V[0], 0, (size_t)N * 4, e->stream));
-    CUX(cudaMemsetAsync(e->d_V[1], 0, (size_t)N * 4, e->stream));
+    CUX(cudaMemsetAsync(e->d_V[0], 0, (size_t)N * 4 + 32, e->stream));
+    CUX(cudaMemsetAsync(e->d_V[1], 0, (size_t)N * 4 + 32, e->stream));
     CUX(cudaMemsetAsync(e->d_policy, 0, (size_t)e->n_pad * 4, e->stream));
     CUX(cudaMemsetAsync(e->d_term, 0, (size_t)e->n_pad, e->stream));
     CUX(cudaMemsetAsync(e->d_ctl, 0, sizeof(pi::Ctl), e->stream));
@@ -472,6 +607,18 @@ int pi_create(const pi_grid* grid, const float* actions, int32_t n_actions, cons
         CUX(cudaMemcpyAsync(e->d_axes[d], grid->axes[d], (size_t)grid->shape[d] * 4, cudaMemcpyHostToDevice, e->stream));
     }
     CUX(cudaStreamSynchronize(e->stream));
+    rc = choose_layout(e);
+    if (rc) { pi_destroy(e); return rc; }
+    {
+        bool ok = false;
+        DISPATCH_D(e, query_pair_supported, e, &ok);
+        const char* kenv = getenv("DPB200_EVAL_KERNEL");  // scalar | pair (default: pair when supported)
+        e->pair_kernel = ok && (kenv && !strcmp(kenv, "pair"));  // opt-in: the persistent scalar kernel is faster today
+        cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+        DISPATCH_D(e, query_eval_occupancy, e, &e->blocks_per_sm);  // persistent grid = resident blocks
+        e->lookahead = e->sm_count * e->blocks_per_sm;
+        if (const char* b = getenv("DPB200_LOOKAHEAD")) e->lookahead = std::max(0, atoi(b));
+    }
 
     if (e->world > 1) {
         if (!g_nccl.load()) { pi_destroy(e); return fail(PI_ERR_COMM, "libnccl.so.2 could not be loaded: %s", dlerror()); }
@@ -494,7 +641,7 @@ void pi_destroy(pi_engine* e) {
             if (gx) cudaGraphExecDestroy(gx);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     cudaFree(e->d_V[0]); cudaFree(e->d_V[1]); cudaFree(e->d_policy); cudaFree(e->d_term);
-    cudaFree(e->d_mask_full); cudaFree(e->d_table); cudaFree(e->d_rows); cudaFree(e->d_actions);
+    cudaFree(e->d_mask_full); cudaFree(e->d_scratch); cudaFree(e->d_table); cudaFree(e->d_rows); cudaFree(e->d_actions);
     cudaFree(e->d_ctl); cudaFree(e->d_partial); cudaFree(e->d_delta_g); cudaFree(e->d_changed_g);
     for (auto& a : e->d_axes) cudaFree(a);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
@@ -526,9 +673,10 @@ int pi_set_terminal(pi_engine* e, const uint8_t* mask, float value) {
     CU(cudaSetDevice(e->device));
     int rc = upload_mask(e, mask);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(e->d_term, e->d_mask_full + e->s_begin, (size_t)e->n_local, cudaMemcpyDeviceToDevice, e->stream));
-    pi::fill_masked_kernel<<<nblocks(e->N), pi::kBlock, 0, e->stream>>>(e->d_V[0], e->d_V[1], e->d_mask_full, e->N, value);
-    e->launches++;
+    pi::to_internal_kernel<unsigned char><<<nblocks(e->n_local), pi::kBlock, 0, e->stream>>>(e->g, e->d_mask_full, e->d_term,
+                                                                                        e->s_begin, e->n_local);
+    pi::fill_masked_kernel<<<nblocks(e->N), pi::kBlock, 0, e->stream>>>(e->g, e->d_V[0], e->d_V[1], e->d_mask_full, e->N, value);
+    e->launches += 2;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
     return PI_OK;
@@ -539,7 +687,7 @@ int pi_set_values(pi_engine* e, const uint8_t* mask, float value) {
     CU(cudaSetDevice(e->device));
     int rc = upload_mask(e, mask);
     if (rc) return rc;
-    pi::fill_masked_kernel<<<nblocks(e->N), pi::kBlock, 0, e->stream>>>(e->d_V[0], e->d_V[1], e->d_mask_full, e->N, value);
+    pi::fill_masked_kernel<<<nblocks(e->N), pi::kBlock, 0, e->stream>>>(e->g, e->d_V[0], e->d_V[1], e->d_mask_full, e->N, value);
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
@@ -549,28 +697,11 @@ int pi_set_values(pi_engine* e, const uint8_t* mask, float value) {
 int pi_build_table(pi_engine* e) {
     if (!e) return fail(PI_ERR_INVALID, "null engine");
     CU(cudaSetDevice(e->device));
-    // pack PiBuildParams (natural alignment, arrays of PI_D entries)
-    std::vector<unsigned char> b;
-    put(b, e->d_table, 8);
-    const float* act = e->d_actions;
-    put(b, act, 8);
-    const unsigned char* term = e->d_term;
-    put(b, term, 8);
-    for (int d = 0; d < e->D; ++d) { const float* ax = e->d_axes[d]; put(b, ax, 8); }
-    put(b, e->n_local, 8);
-    put(b, e->n_pad, 8);
-    put(b, e->s_begin, 8);
-    put(b, e->A, 4);
-    for (int d = 0; d < e->D; ++d) put(b, e->g.shape[d], 4);
-    for (int d = 0; d < e->D; ++d) put(b, e->g.stride[d], 4);
-    for (int d = 0; d < e->D; ++d) put(b, e->g.lo[d], 4);
-    for (int d = 0; d < e->D; ++d) put(b, e->g.hi[d], 4);
-    while (b.size() % 8) b.push_back(0);
-    void* args[] = {b.data()};
     CU(cudaEventRecord(e->ev_t0, e->stream));
-    dim3 grid(nblocks(e->n_local), (unsigned)e->A, 1);
-    CU(cudaLaunchKernel((const void*)e->build_kernel, grid, dim3(pi::kBlock, 1, 1), args, 0, e->stream));
-    e->launches++;
+    {
+        int rc = launch_build(e, e->d_table, e->d_actions, e->A, e->d_term, e->n_local, e->n_pad, e->s_begin);
+        if (rc) return rc;
+    }
     DISPATCH_D(e, launch_compact, e);
     e->launches++;
     CU(cudaEventRecord(e->ev_t1, e->stream));
@@ -586,8 +717,8 @@ int pi_build_table(pi_engine* e) {
     }
     int rc = build_graphs(e);
     if (rc) return rc;
-    logf(e, 1, "Transition table: %lld states x %d actions, %.1f MB, built in %.3f ms", e->n_local, e->A,
-         (double)pi_table_bytes(e) / 1048576.0, ms);
+    logf(e, 1, "Transition table: %lld states x %d actions, %.1f MB, built in %.3f ms (storage: dim %d fastest)",
+         e->n_local, e->A, (double)pi_table_bytes(e) / 1048576.0, ms, e->fast_dim);
     return PI_OK;
 }
 
@@ -730,18 +861,31 @@ static int gather_full_values(pi_engine* e) {
     return PI_OK;
 }
 
+static int need_scratch(pi_engine* e) {
+    if (!e->d_scratch) CU(cudaMalloc(&e->d_scratch, (size_t)e->N * 4));
+    return PI_OK;
+}
+
 int pi_copy_results(pi_engine* e, float* value_function, int32_t* policy) {
     if (!e) return fail(PI_ERR_INVALID, "null engine");
     CU(cudaSetDevice(e->device));
+    if (!e->identity_layout) { int rc = need_scratch(e); if (rc) return rc; }
     if (value_function) {
         int rc = gather_full_values(e);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(value_function, e->d_V[e->cur], (size_t)e->N * 4, cudaMemcpyDeviceToHost, e->stream));
+        const float* src = e->d_V[e->cur];
+        if (!e->identity_layout) {  // internal storage order -> reference order
+            pi::to_reference_kernel<float><<<nblocks(e->N), pi::kBlock, 0, e->stream>>>(
+                e->g, e->d_V[e->cur], static_cast<float*>(e->d_scratch), e->N);
+            e->launches++;
+            src = static_cast<float*>(e->d_scratch);
+        }
+        CU(cudaMemcpyAsync(value_function, src, (size_t)e->N * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
     }
     if (policy) {
-        if (e->world == 1) {
-            CU(cudaMemcpyAsync(policy, e->d_policy, (size_t)e->N * 4, cudaMemcpyDeviceToHost, e->stream));
-        } else {
+        const int* full = e->d_policy;  // single GPU: the local slice is everything
+        if (e->world > 1) {
             // gather the policy slices through the spare V buffer (same element size)
             int* buf = reinterpret_cast<int*>(e->d_V[e->cur ^ 1]);
             CU(cudaMemcpyAsync(buf + e->s_begin, e->d_policy, (size_t)e->n_local * 4, cudaMemcpyDeviceToDevice, e->stream));
@@ -753,8 +897,15 @@ int pi_copy_results(pi_engine* e, float* value_function, int32_t* policy) {
                 NC(g_nccl.Recv(buf + lo, (size_t)(hi - lo), ncclInt32, r, e->comm, e->stream));
             }
             NC(g_nccl.GroupEnd());
-            CU(cudaMemcpyAsync(policy, buf, (size_t)e->N * 4, cudaMemcpyDeviceToHost, e->stream));
+            full = buf;
         }
+        if (!e->identity_layout) {
+            pi::to_reference_kernel<int><<<nblocks(e->N), pi::kBlock, 0, e->stream>>>(
+                e->g, full, static_cast<int*>(e->d_scratch), e->N);
+            e->launches++;
+            full = static_cast<int*>(e->d_scratch);
+        }
+        CU(cudaMemcpyAsync(policy, full, (size_t)e->N * 4, cudaMemcpyDeviceToHost, e->stream));
     }
     CU(cudaStreamSynchronize(e->stream));
     return PI_OK;
@@ -775,7 +926,16 @@ int pi_upload_policy(pi_engine* e, const int32_t* policy) {
     if (!e || !policy) return fail(PI_ERR_INVALID, "null argument");
     if (!e->table_built) return fail(PI_ERR_INVALID, "pi_build_table has not been called");
     CU(cudaSetDevice(e->device));
-    CU(cudaMemcpyAsync(e->d_policy, policy + e->s_begin, (size_t)e->n_local * 4, cudaMemcpyHostToDevice, e->stream));
+    if (e->identity_layout) {
+        CU(cudaMemcpyAsync(e->d_policy, policy + e->s_begin, (size_t)e->n_local * 4, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        int rc = need_scratch(e);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(e->d_scratch, policy, (size_t)e->N * 4, cudaMemcpyHostToDevice, e->stream));
+        pi::to_internal_kernel<int><<<nblocks(e->n_local), pi::kBlock, 0, e->stream>>>(
+            e->g, static_cast<const int*>(e->d_scratch), e->d_policy, e->s_begin, e->n_local);
+        e->launches++;
+    }
     DISPATCH_D(e, launch_compact, e);
     e->launches++;
     CU(cudaGetLastError());
@@ -786,7 +946,17 @@ int pi_upload_policy(pi_engine* e, const int32_t* policy) {
 int pi_upload_values(pi_engine* e, const float* v) {
     if (!e || !v) return fail(PI_ERR_INVALID, "null argument");
     CU(cudaSetDevice(e->device));
-    CU(cudaMemcpyAsync(e->d_V[e->cur], v, (size_t)e->N * 4, cudaMemcpyHostToDevice, e->stream));
+    if (e->identity_layout) {
+        CU(cudaMemcpyAsync(e->d_V[e->cur], v, (size_t)e->N * 4, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        int rc = need_scratch(e);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(e->d_scratch, v, (size_t)e->N * 4, cudaMemcpyHostToDevice, e->stream));
+        pi::to_internal_kernel<float><<<nblocks(e->N), pi::kBlock, 0, e->stream>>>(
+            e->g, static_cast<const float*>(e->d_scratch), e->d_V[e->cur], 0, e->N);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(e->stream));
     e->results_gathered = true;
     return PI_OK;
@@ -828,9 +998,9 @@ int pi_expand_rows(pi_engine* e, int32_t action, int64_t s_begin, int64_t count,
     if (!e) return fail(PI_ERR_INVALID, "null engine");
     if (!e->table_built) return fail(PI_ERR_INVALID, "pi_build_table has not been called");
     if (action < 0 || action >= e->A) return fail(PI_ERR_INVALID, "action out of range");
-    if (s_begin < e->s_begin || s_begin + count > e->s_end || count < 0)
-        return fail(PI_ERR_INVALID, "state range [%lld,%lld) outside this shard [%lld,%lld)", (long long)s_begin,
-                    (long long)(s_begin + count), e->s_begin, e->s_end);
+    if (s_begin < 0 || s_begin + count > e->N || count < 0)
+        return fail(PI_ERR_INVALID, "state range [%lld,%lld) outside the grid [0,%lld)", (long long)s_begin,
+                    (long long)(s_begin + count), e->N);
     if (count == 0) return PI_OK;
     CU(cudaSetDevice(e->device));
     const int C = 1 << e->D;
@@ -839,7 +1009,7 @@ int pi_expand_rows(pi_engine* e, int32_t action, int64_t s_begin, int64_t count,
     if (w) CU(cudaMalloc(&d_w, (size_t)count * C * 4));
     if (reward) CU(cudaMalloc(&d_r, (size_t)count * 4));
     if (terminated) CU(cudaMalloc(&d_t, (size_t)count));
-    DISPATCH_D(e, launch_expand, e, action, s_begin - e->s_begin, count, d_idx, d_w, d_r, d_t);
+    DISPATCH_D(e, launch_expand, e, action, s_begin, count, d_idx, d_w, d_r, d_t);
     e->launches++;
     CU(cudaGetLastError());
     if (idx) CU(cudaMemcpyAsync(idx, d_idx, (size_t)count * C * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -857,6 +1027,16 @@ int pi_device_ptrs(pi_engine* e, void** v, void** nv, void** policy, void** term
     if (nv) *nv = e->d_V[e->cur ^ 1];
     if (policy) *policy = e->d_policy;
     if (term) *term = e->d_term;
+    return PI_OK;
+}
+
+int pi_layout(const pi_engine* e, int32_t* fast_dim, int32_t perm[PI_MAX_DIMS], double probe_lines[PI_MAX_DIMS]) {
+    if (!e) return fail(PI_ERR_INVALID, "null engine");
+    if (fast_dim) *fast_dim = e->fast_dim;
+    for (int d = 0; d < PI_MAX_DIMS; ++d) {
+        if (perm) perm[d] = d < e->D ? e->g.perm[d] : -1;
+        if (probe_lines) probe_lines[d] = d < e->D ? e->probe_lines[d] : 0.0;
+    }
     return PI_OK;
 }
 
@@ -915,7 +1095,7 @@ int compute_exchange_plan(pi_engine* e) {
     CU(cudaMemcpyAsync(d_lo, lo.data(), Wd * 8, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(d_hi, hi.data(), Wd * 8, cudaMemcpyHostToDevice, e->stream));
     int span = 0;
-    for (int d = 0; d < e->D; ++d) span += e->g.stride[d];
+    for (int d = 0; d < e->D; ++d) span += e->g.istride[d];
     need_ranges_kernel<<<nblocks(e->n_local), pi::kBlock, 0, e->stream>>>(e->d_table, e->n_pad, e->n_local, e->A,
                                                                         e->D + 2, span, e->N, Wd, d_lo, d_hi);
     e->launches++;

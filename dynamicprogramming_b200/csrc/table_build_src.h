@@ -37,9 +37,10 @@ struct PiBuildParams {
     long long s_begin;             // first global state of this shard
     int n_actions;
     int shape[PI_D];
-    int stride[PI_D];
+    int stride[PI_D];              // INTERNAL storage strides, indexed by logical dimension
     float lo[PI_D];
     float hi[PI_D];
+    int perm[PI_D];                // storage position (0 = slowest) -> logical dimension
 };
 
 __device__ __forceinline__ void pi_st16(void* p, unsigned a, unsigned b, unsigned c, unsigned d) {
@@ -65,14 +66,17 @@ extern "C" __global__ void __launch_bounds__(256) pi_build_rows(const PiBuildPar
     if (p.absorbing != nullptr && p.absorbing[pi_s]) {
         pi_w[0] = (unsigned)(-2);                       // PI_ROW_ABSORBING
     } else {
-        // flat index -> node coordinates (dim 0 slowest, dim D-1 stride 1)
+        // internal flat index -> node coordinates (storage position k holds dimension perm[k])
         float pi_x[PI_D];
         unsigned pi_r = (unsigned)(p.s_begin + pi_s);
         #pragma unroll
-        for (int d = PI_D - 1; d >= 0; --d) {
-            const unsigned pi_q = pi_r / (unsigned)p.shape[d];
-            const unsigned pi_i = pi_r - pi_q * (unsigned)p.shape[d];
-            pi_x[d] = p.axes[d][pi_i];
+        for (int k = PI_D - 1; k >= 0; --k) {
+            const int pi_d = p.perm[k];
+            const unsigned pi_q = pi_r / (unsigned)p.shape[pi_d];
+            const unsigned pi_i = pi_r - pi_q * (unsigned)p.shape[pi_d];
+            #pragma unroll
+            for (int d = 0; d < PI_D; ++d)
+                if (d == pi_d) pi_x[d] = p.axes[d][pi_i];
             pi_r = pi_q;
         }
         const float pi_action = p.actions[pi_a];

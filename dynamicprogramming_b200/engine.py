@@ -371,12 +371,29 @@ class _CudaPolicyIterationBase(abc.ABC):
         self._refresh_device_handles()
         return float(delta.value), float(ms.value)
 
+    def layout(self) -> dict:
+        """Internal storage order chosen by the engine (include/dpb200.h: pi_layout).
+        Host-facing arrays are always in reference order; only the raw device
+        handles (d_value_function, ...) are stored with `fast_dim` contiguous."""
+        fast = C.c_int32()
+        perm = (C.c_int32 * _ffi.PI_MAX_DIMS)()
+        lines = (C.c_double * _ffi.PI_MAX_DIMS)()
+        _ffi.check(_ffi.lib().pi_layout(self._engine, C.byref(fast), perm, lines))
+        D = self.N_DIMS
+        return {"fast_dim": int(fast.value), "perm": [int(perm[k]) for k in range(D)],
+                "probe_lines": [float(lines[d]) for d in range(D)]}
+
+    def to_internal_order(self, ref_array: np.ndarray) -> np.ndarray:
+        """Reorder a reference-order (n_states,) array into the engine's storage order."""
+        perm = self.layout()["perm"]
+        return np.ascontiguousarray(np.asarray(ref_array).reshape(tuple(self.grid_shape)).transpose(perm)).ravel()
+
     def expand_rows(self, action: int, s_begin: int = 0, count: int | None = None):
         """(idx, w, reward, terminated) in the reference's corner form, for parity checks."""
         self.build_table()
         lib = _ffi.lib()
         if count is None:
-            count = lib.pi_local_end(self._engine) - s_begin
+            count = self.n_states - s_begin
         Cn = 1 << self.N_DIMS
         idx = np.empty((count, Cn), dtype=np.int32)
         w = np.empty((count, Cn), dtype=np.float32)

@@ -151,7 +151,8 @@ int pi_run(pi_engine* e, pi_stats* stats);
  * policy (n_states each) to host.  Multi-GPU: collective, every rank gets all. */
 int pi_copy_results(pi_engine* e, float* value_function, int32_t* policy);
 
-/* This rank's slice only (states [pi_local_begin, pi_local_end)); no collective. */
+/* This rank's slice only (internal states [pi_local_begin, pi_local_end), in the
+ * engine's storage order, see pi_layout); no collective. */
 int pi_copy_local_results(pi_engine* e, float* value_function_local, int32_t* policy_local);
 
 /* Host <-> device hand-off used by the end-to-end evaluation call and tests. */
@@ -175,6 +176,16 @@ int pi_expand_rows(pi_engine* e, int32_t action, int64_t s_begin, int64_t count,
  * (d_value_function, d_policy, ... of the reference object). */
 int pi_device_ptrs(pi_engine* e, void** value_function, void** new_value_function,
                    void** policy, void** terminal_mask);
+
+/* Internal storage order.  The engine may store states with a
+ * different dimension fastest than the reference does (chosen by a build-time
+ * probe of gather coalescing; DPB200_FAST_DIM=ref|auto|<dim> overrides).  Every
+ * host-facing call above takes and returns REFERENCE order; only the raw
+ * device pointers and pi_copy_local_results expose the internal order.
+ * perm[k] = logical dimension stored at position k (0 = slowest);
+ * probe_lines[d] = measured 128-byte lines per warp gather with d fastest. */
+int pi_layout(const pi_engine* e, int32_t* fast_dim, int32_t perm[PI_MAX_DIMS],
+              double probe_lines[PI_MAX_DIMS]);
 
 /* Geometry queries. */
 int64_t pi_n_states(const pi_engine* e);

@@ -1,0 +1,52 @@
+#!/usr/bin/env python3
+"""torchrun --nproc-per-node N scripts/multi_gpu_check.py — sharded == unsharded, bit for bit.
+
+Every rank builds its shard; rank 0 additionally runs the same problem unsharded
+and compares V, policy, PI iterations and sweep counts (SURVEY §8e invariant)."""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from loguru import logger
+
+logger.remove()
+import torch
+
+from dynamicprogramming_b200 import _ffi, dist as pdist, envs
+
+rank = int(os.environ.get("RANK", 0))
+world = int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+td = pdist.init_process_group()
+cases = [("cartpole", 12, 4), ("mountain_car", 60, None), ("double_pendulum_swingup", 10, 3),
+         ("double_cartpole_swingup", 7, 2), ("pendulum", 33, 6)]
+ok = True
+for env, bins, max_pi in cases:
+    spec = envs.REGISTRY[env]
+    cfg = spec.config()
+    if max_pi:
+        cfg.max_pi_iter = max_pi
+    shard = pdist.make_shard(local)
+    eng = spec.make(bins=bins, config=cfg, device=local, shard=shard)
+    eng.run()
+    res = dict(env=env, bins=bins, N=eng.n_states, pi=eng.pi_iterations, sweeps=eng.total_eval_sweeps)
+    if rank == 0:
+        one = spec.make(bins=bins, config=cfg, device=local)
+        one.run()
+        res.update(pi_1gpu=one.pi_iterations, sweeps_1gpu=one.total_eval_sweeps,
+                   policy_diff=int(np.sum(one.policy != eng.policy)),
+                   v_bitdiff=int(np.sum(one.value_function.view(np.uint32) != eng.value_function.view(np.uint32))))
+        good = (res["policy_diff"] == 0 and res["v_bitdiff"] == 0 and res["pi"] == res["pi_1gpu"]
+                and res["sweeps"] == res["sweeps_1gpu"])
+        ok &= good
+        print(("OK   " if good else "FAIL ") + json.dumps(res), flush=True)
+    td.barrier()
+flag = torch.tensor([1 if ok else 0], device="cuda")
+td.broadcast(flag, src=0)
+td.destroy_process_group()
+sys.exit(0 if int(flag.item()) else 1)

@@ -21,5 +21,5 @@ eng.build_table()
 for _ in range(a.improve):
     eng.policy_improvement()
 d, ms = eng.sweeps(a.sweeps)
-print(f"{a.env}@{a.bins}: {ms / a.sweeps:.4f} ms/sweep, {eng.n_states / (ms / a.sweeps) / 1e6:.2f} G backups/s, delta={d}")
+print(eng.layout()); print(f"{a.env}@{a.bins}: {ms / a.sweeps:.4f} ms/sweep, {eng.n_states / (ms / a.sweeps) / 1e6:.2f} G backups/s, delta={d}")
 eng.close()

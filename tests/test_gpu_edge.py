@@ -127,8 +127,11 @@ def test_host_device_handoff_and_device_handles():
     np.testing.assert_array_equal(p2, P)
     t = torch.as_tensor(eng.d_value_function, device="cuda")          # zero-copy view through __cuda_array_interface__
     assert t.shape == (N,) and t.dtype == torch.float32
-    np.testing.assert_array_equal(t.cpu().numpy(), V)
-    np.testing.assert_array_equal(eng.d_policy.get(), P)
+    # raw device handles are in the engine's storage order (pi_layout); host calls are in reference order
+    np.testing.assert_array_equal(t.cpu().numpy(), eng.to_internal_order(V))
+    np.testing.assert_array_equal(eng.d_policy.get(), eng.to_internal_order(P))
+    lay = eng.layout()
+    assert sorted(lay["perm"]) == list(range(4)) and lay["perm"][-1] == lay["fast_dim"]
     eng.close()
 
 
@@ -172,3 +175,29 @@ def test_saved_file_from_a_gpu_run(tmp_path):
     assert d["policy"].dtype == np.int32 and d["value_function"].dtype == np.float32
     again = type(eng).load(tmp_path / "mc.npz")
     np.testing.assert_array_equal(again.policy, eng.policy)
+
+
+@pytest.mark.parametrize("fast", ["ref", "0", "1", "auto"])
+def test_storage_order_never_changes_results(fast, ref_runner, monkeypatch):
+    """Whatever dimension the engine stores contiguously, rows, V and policy stay bit-identical."""
+    monkeypatch.setenv("DPB200_FAST_DIM", fast)
+    spec = envs.REGISTRY["double_cartpole_swingup"]
+    cfg = spec.config()
+    cfg.max_pi_iter = 2
+    eng = spec.make(bins=5, config=cfg)
+    lay = eng.layout()
+    if fast in ("0", "1"):
+        assert lay["fast_dim"] == int(fast)
+    if fast == "ref":
+        assert lay["fast_dim"] == 5
+    ref = ref_runner.from_engine_env("double_cartpole_swingup", bins=5, config=cfg)
+    idx, w, r, t = eng.expand_rows(3)
+    ridx, rw, rr, rt, _ = ref.probe_rows(3)
+    live = (t != 2) & (rt == 0) & (t == 0)
+    np.testing.assert_array_equal(idx[live], ridx[live])
+    np.testing.assert_array_equal(bits(w[live]), bits(rw[live]))
+    eng.run()
+    ref.run()
+    assert eng.total_eval_sweeps == ref.total_sweeps
+    np.testing.assert_array_equal(eng.policy, ref.policy)
+    np.testing.assert_array_equal(bits(eng.value_function), bits(ref.value_function))
