@@ -178,6 +178,7 @@ def run_ours(args) -> dict:
         dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
     value = N * SWEEPS_PER_STEP / (ms_per_step * 1e-3)
+    kinfo = eng.eval_kernel_info()   # which sweep kernel the engine runs for THIS policy (scalar gather / x-line)
 
     # ---- end-to-end arm: host buffers in, host buffers out ---------------------
     n_local = hi - lo
@@ -230,7 +231,7 @@ def run_ours(args) -> dict:
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.bins), "kernel": f"pi::eval_sweep_kernel<{D}>",
+                         "traffic": ncu_traffic(args.bins), "kernel": kinfo["kernel"],
                          "peak_source": peak_src, "layout": "compact row (base + D fractions + reward)",
                          "algorithmic_bytes_per_backup": bytes_per_backup,
                          "survey_gather_counted_bytes_per_backup": (D + 2) * 4 + 4 * (1 << D) + 13,

@@ -46,7 +46,18 @@ def needs_rebuild() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def stringify_jit_sources() -> None:
+    """csrc/*_src.cuh (kernels compiled at run time by NVRTC) -> csrc/*_src.inc raw-string
+    literals that dpb200.cu #includes."""
+    for src in CSRC.glob("*_src.cuh"):
+        inc = src.with_suffix(".inc")
+        text = 'R"XLSRC(\n' + src.read_text() + '\n)XLSRC"\n'
+        if not inc.exists() or inc.read_text() != text:
+            inc.write_text(text)
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    stringify_jit_sources()
     if not force and not needs_rebuild():
         return LIB
     cuda_lib = Path(_nvcc()).resolve().parents[1] / "lib64"

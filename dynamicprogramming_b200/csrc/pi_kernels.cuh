@@ -240,6 +240,36 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// How regular are the rows of the current policy along the fast-stored dimension?  A group of K
+// consecutive states is regular when every live state has base_j - j == A with A % K in {0, K-1}
+// (the window condition of the x-line sweep, xline_sweep_src.cuh).  Called by all threads of a
+// block whose thread index == local state index modulo 32 (groups never straddle a warp);
+// counters: [0] pairs, [1] regular pairs, [2] quads, [3] regular quads.
+__device__ __forceinline__ void count_regular_groups(int base, bool in, unsigned long long* counters) {
+    if (counters == nullptr) return;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool live = base >= 0;
+    const unsigned livem = __ballot_sync(full, live);
+#pragma unroll
+    for (int K = 2; K <= 4; K += 2) {
+        const int j = lane % K;
+        const unsigned gmask = ((1u << K) - 1u) << (lane - j);
+        const unsigned lm = livem & gmask;
+        const int t = base - j;
+        const int A = __shfl_sync(full, t, lm ? __ffs(lm) - 1 : lane);
+        const unsigned okm = __ballot_sync(full, !live || t == A) & gmask;
+        const int m = A & (K - 1);
+        const bool regular = lm == 0 || (okm == gmask && (m == 0 || m == K - 1));
+        const unsigned heads = __ballot_sync(full, in && j == 0);
+        const unsigned regs = __ballot_sync(full, in && j == 0 && regular);
+        if (lane == 0 && heads) {
+            atomicAdd(counters + (K - 2), (unsigned long long)__popc(heads));
+            atomicAdd(counters + (K - 1), (unsigned long long)__popc(regs));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Evaluation sweep: one Jacobi Bellman backup of every local state with the
 // residual fused in (replaces policy_eval_kernel* + the max_abs_diff
@@ -613,6 +643,7 @@ struct ImproveParams {
     const float* V;              // current value function (full length)
     int* policy;                 // local policy (n_local)
     unsigned int* partial;       // per-block count of states whose action changed
+    unsigned long long* regular; // optional: regularity counters of the new policy's rows (count_regular_groups)
     long long n_local;
     long long n_pad;
     int n_actions;
@@ -624,6 +655,7 @@ template <int D>
 __global__ void __launch_bounds__(kBlock) improve_kernel(const ImproveParams p) {
     const long long s = (long long)blockIdx.x * kBlock + threadIdx.x;
     int changed = 0;
+    int win_base = PI_ROW_ABSORBING;
     if (s < p.n_local) {
         constexpr int W = Row<D>::W;
         const size_t a_stride = (size_t)W * 4u * (size_t)p.n_pad;
@@ -661,7 +693,9 @@ __global__ void __launch_bounds__(kBlock) improve_kernel(const ImproveParams p) 
             changed = (best_a != old_a);
         }
         store_row<D>(p.rows, p.n_pad, s, best_row);
+        win_base = (int)best_row[0];
     }
+    count_regular_groups(win_base, s < p.n_local, p.regular);
     const unsigned m = __ballot_sync(0xffffffffu, changed);
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
@@ -690,13 +724,17 @@ __global__ void __launch_bounds__(1024) count_reduce_kernel(Ctl* ctl, const unsi
 template <int D>
 __global__ void __launch_bounds__(kBlock) compact_rows_kernel(const unsigned char* table, unsigned char* rows,
                                                               const int* policy, long long n_local,
-                                                              long long n_pad) {
+                                                              long long n_pad, unsigned long long* regular) {
     const long long s = (long long)blockIdx.x * kBlock + threadIdx.x;
-    if (s >= n_local) return;
-    constexpr int W = Row<D>::W;
-    unsigned w[W];
-    load_row<D>(table + (size_t)policy[s] * ((size_t)W * 4u * (size_t)n_pad), n_pad, s, w);
-    store_row<D>(rows, n_pad, s, w);
+    int base = PI_ROW_ABSORBING;
+    if (s < n_local) {
+        constexpr int W = Row<D>::W;
+        unsigned w[W];
+        load_row<D>(table + (size_t)policy[s] * ((size_t)W * 4u * (size_t)n_pad), n_pad, s, w);
+        store_row<D>(rows, n_pad, s, w);
+        base = (int)w[0];
+    }
+    count_regular_groups(base, s < n_local, regular);
 }
 
 // Expand compact rows to the reference's corner form (parity checks only).
@@ -774,6 +812,52 @@ __global__ void gather_lines_kernel(const unsigned char* table, int first_plane_
             atomicAdd(warps, 1ull);
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// x-line sweep support (the sweep itself is JIT-compiled from xline_sweep_src.cuh).
+// Tile order: the non-fast storage positions k = 0..D-2 are cut into tiles of T_k nodes;
+// tiles are enumerated lexicographically (position 0 slowest), the x-lines of a tile
+// lexicographically inside it, the S states of an x-line last.
+// ---------------------------------------------------------------------------
+struct TileGeo {
+    int n_pos;               // D - 1
+    int n_l;                 // x-lines per tile
+    int S;                   // states per x-line
+    int ntile[kMaxDims];     // tiles per position
+    int tline[kMaxDims];     // V-line step between consecutive tiles of a position
+};
+
+// rows (16-byte planes, local V order)  ->  word-SoA planes in tile order.  One thread per row.
+template <int D>
+__global__ void __launch_bounds__(kBlock) retile_rows_kernel(const unsigned char* __restrict__ src, long long n_pad_src,
+                                                             long long s_begin, unsigned* __restrict__ dst,
+                                                             long long plane_words, const int* __restrict__ line_off,
+                                                             TileGeo geo, long long tile_begin, long long n_rows) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const long long per_tile = (long long)geo.n_l * geo.S;
+    const long long tile = r / per_tile;
+    const int rem = (int)(r - tile * per_tile);
+    const int xl = rem / geo.S, x = rem - xl * geo.S;
+    long long t = tile_begin + tile, line = 0;
+    for (int k = geo.n_pos - 1; k >= 0; --k) {
+        const long long q = t / geo.ntile[k];
+        line += (t - q * geo.ntile[k]) * (long long)geo.tline[k];
+        t = q;
+    }
+    const long long v = (line + line_off[xl]) * (long long)geo.S + x;
+    unsigned w[Row<D>::W];
+    load_row<D>(src, n_pad_src, v - s_begin, w);
+#pragma unroll
+    for (int k = 0; k < Row<D>::W; ++k) dst[(size_t)k * (size_t)plane_words + (size_t)r] = w[k];
+}
+
+__global__ void count_mismatch_kernel(const unsigned* a, const unsigned* b, long long n, unsigned long long* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = i < n && a[i] != b[i];
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
 
 }  // namespace pi

@@ -383,6 +383,25 @@ class _CudaPolicyIterationBase(abc.ABC):
         return {"fast_dim": int(fast.value), "perm": [int(perm[k]) for k in range(D)],
                 "probe_lines": [float(lines[d]) for d in range(D)]}
 
+    def eval_kernel_info(self) -> dict:
+        """Which evaluation-sweep kernel the build-time autotune selected (include/dpb200.h:
+        pi_eval_kernel_info): the scalar gather sweep or the JIT-compiled x-line sweep."""
+        buf = C.create_string_buffer(256)
+        ms_s, ms_x = C.c_double(), C.c_double()
+        kind = _ffi.lib().pi_eval_kernel_info(self._engine, buf, 256, C.byref(ms_s), C.byref(ms_x))
+        return {"xline": kind == 1, "kernel": buf.value.decode(), "probe_ms_scalar": ms_s.value,
+                "probe_ms_selected": ms_x.value}
+
+    def debug_xline(self, cfg: str, iters: int = 5) -> dict:
+        """Test hook: run the x-line sweep configuration `cfg` and the scalar sweep on the current
+        rows and V; returns timings and the number of differing V words (must be 0)."""
+        ms_new, ms_base = C.c_float(), C.c_float()
+        mism, wf, info = C.c_int64(), C.c_double(), (C.c_int32 * 4)()
+        _ffi.check(_ffi.lib().pi_debug_xline(self._engine, cfg.encode(), int(iters), C.byref(ms_new), C.byref(ms_base),
+                                             C.byref(mism), C.byref(wf), info))
+        return {"ms_xline": ms_new.value, "ms_scalar": ms_base.value, "mismatches": int(mism.value),
+                "window_fraction": wf.value, "registers": int(info[0]), "grid": int(info[1]), "block": int(info[2])}
+
     def to_internal_order(self, ref_array: np.ndarray) -> np.ndarray:
         """Reorder a reference-order (n_states,) array into the engine's storage order."""
         perm = self.layout()["perm"]

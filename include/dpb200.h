@@ -197,6 +197,21 @@ int64_t pi_launch_count(const pi_engine* e);
 /* Last-stage device timings in ms (build, eval, improve). */
 int pi_get_stats(const pi_engine* e, pi_stats* stats);
 
+/* Evaluation-sweep kernel selection (new; no reference counterpart).  At pi_build_table the
+ * engine times its scalar gather sweep against the x-line sweep (csrc/xline_sweep_src.cuh:
+ * K consecutive states of the fast-stored dimension per thread, vector window loads, packed
+ * fp32 arithmetic, tile-ordered rows; JIT-compiled with the grid geometry as constants) on
+ * the freshly built rows and keeps the faster one; both produce bit-identical V.
+ * DPB200_XLINE = off | auto | [force:]K,LV,PF,warps,minb[,roll]:T0,T1,..[;more] overrides.
+ * pi_eval_kernel_info returns 1 (x-line) / 0 (scalar), a description and the probe timings. */
+int pi_eval_kernel_info(const pi_engine* e, char* buf, int32_t buf_len, double* ms_scalar, double* ms_selected);
+/* Compile-only check of the x-line sweep for a synthetic bins^n_dims grid; needs no GPU. */
+int pi_xline_compile_check(int32_t n_dims, int32_t bins, const char* cfg, int64_t* cubin_bytes);
+/* Test hook: x-line sweep `cfg` vs the scalar sweep on the current rows and V (bitwise
+ * comparison + timings); info = {registers, grid, block, tiles}; engine state unchanged. */
+int pi_debug_xline(pi_engine* e, const char* cfg, int32_t iters, float* ms_xline, float* ms_scalar,
+                   int64_t* mismatches, double* window_fraction, int32_t* info);
+
 /* N2 (next row): batched policy lookup with get_optimal_action semantics
  * (utils/barycentric.py:11-108; float64 arithmetic, corner_bits order).
  * points: n_points x n_dims float32 (host); out: n_points float32 (host). */

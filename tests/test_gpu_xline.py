@@ -1,0 +1,108 @@
+"""The x-line evaluation sweep (csrc/xline_sweep_src.cuh: vector window loads, packed fp32
+arithmetic, tile-ordered rows, JIT-compiled per grid) must be bit-identical to the scalar
+gather sweep — and therefore to the reference's policy_eval_kernel_4d/_6d
+(src/cuda_policy_iteration.py:616-649, :1044-1079) — on every environment, including the
+ones whose successors are NOT consecutive along the fast dimension (scalar fallback path),
+terminated / absorbing rows, clamped edges and wrapped angles."""
+import numpy as np
+import pytest
+
+from dynamicprogramming_b200 import envs
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _prepared(env, bins, monkeypatch, sweeps=7):
+    monkeypatch.setenv("DPB200_FAST_DIM", "0")   # the x-line sweep needs logical dimension 0 stored fastest
+    monkeypatch.setenv("DPB200_XLINE", "off")    # the engine's own sweeps stay scalar: they are the comparison
+    eng = envs.make(env, bins=bins)
+    eng.build_table()
+    eng.policy_improvement()
+    eng.sweeps(sweeps)
+    return eng
+
+
+CASES_6D = [("double_cartpole_swingup", 8), ("double_cartpole", 8)]
+CASES_4D = [("cartpole", 12), ("cartpole_swingup", 16), ("double_pendulum_swingup", 12), ("overhead_crane", 12)]
+
+
+@pytest.mark.parametrize("env,bins", CASES_6D + CASES_4D)
+@pytest.mark.parametrize("cfg", ["2,0,4,8,2,1", "4,0,4,8,1,1", "4,0,2,4,1,2", "2,1,2,4,2,4", "4,1,4,8,1,1"])
+def test_xline_sweep_is_bit_identical_to_the_scalar_sweep(env, bins, cfg, monkeypatch):
+    eng = _prepared(env, bins, monkeypatch)
+    D = eng.N_DIMS
+    K, warps = int(cfg.split(",")[0]), int(cfg.split(",")[3])
+    # tile: fill the CTA's x-line slots from the fastest non-fast position
+    slots, tile = warps * (32 // (bins // K)), [1] * (D - 1)
+    for k in range(D - 2, -1, -1):
+        t = max(d for d in range(1, bins + 1) if bins % d == 0 and d <= slots)
+        tile[k] = t
+        slots //= t
+    out = eng.debug_xline(cfg + ":" + ",".join(map(str, tile)), iters=1)
+    assert out["mismatches"] == 0, out
+    eng.close()
+
+
+@pytest.mark.parametrize("env,bins,cfg", [("double_cartpole_swingup", 8, "force:4,0,4,8,1,1:1,1,2,4,4"),
+                                          ("cartpole", 12, "force:2,0,4,8,2,1:1,3,6"),
+                                          ("double_pendulum_swingup", 12, "force:4,0,4,8,1,1:2,4,6")])
+def test_full_policy_iteration_with_the_xline_sweep_matches_the_reference(env, bins, cfg, monkeypatch, ref_runner):
+    """Complete run() with the x-line sweep forced on: PI iterations, sweep counts, policy and V bits
+    equal the reference's own kernels."""
+    monkeypatch.setenv("DPB200_FAST_DIM", "0")
+    monkeypatch.setenv("DPB200_XLINE", cfg)
+    spec = envs.REGISTRY[env]
+    c = spec.config()
+    c.max_pi_iter, c.max_eval_iter = 4, 300
+    eng = spec.make(bins=bins, config=c)
+    eng.build_table()
+    info = eng.eval_kernel_info()
+    assert info["xline"], info
+    ref = ref_runner.from_engine_env(env, bins=bins, config=c)
+    eng.run()
+    ref.run()
+    assert eng.total_eval_sweeps == ref.total_sweeps and eng.pi_iterations == ref.pi_iterations
+    np.testing.assert_array_equal(eng.policy, ref.policy)
+    np.testing.assert_array_equal(bits(eng.value_function), bits(ref.value_function))
+
+
+def test_autotune_reports_its_choice_and_never_changes_results(monkeypatch):
+    runs = {}
+    for mode in ("off", "auto"):
+        monkeypatch.setenv("DPB200_XLINE", mode)
+        spec = envs.REGISTRY["double_cartpole_swingup"]
+        c = spec.config()
+        c.max_pi_iter, c.max_eval_iter = 2, 120
+        eng = spec.make(bins=8, config=c)
+        eng.build_table()
+        info = eng.eval_kernel_info()   # before run(): run() releases the device side like the reference
+        assert info["kernel"] and (mode == "auto" or not info["xline"])
+        eng.run()
+        runs[mode] = (eng.total_eval_sweeps, eng.policy.copy(), bits(eng.value_function).copy())
+        eng.close()
+    assert runs["off"][0] == runs["auto"][0]
+    np.testing.assert_array_equal(runs["off"][1], runs["auto"][1])
+    np.testing.assert_array_equal(runs["off"][2], runs["auto"][2])
+
+
+def test_upload_policy_refreshes_the_tile_ordered_rows(monkeypatch):
+    """pi_upload_policy re-compacts AND re-tiles: sweeps after an upload use the new policy's rows."""
+    monkeypatch.setenv("DPB200_FAST_DIM", "0")
+    res = {}
+    for mode in ("off", "force:2,0,4,8,2,1:1,1,1,2,4"):
+        monkeypatch.setenv("DPB200_XLINE", mode)
+        eng = envs.make("double_cartpole_swingup", bins=8)
+        eng.build_table()
+        rng = np.random.default_rng(5)
+        eng.upload_policy(rng.integers(0, eng.n_actions, eng.n_states).astype(np.int32))
+        eng.sweeps(5)
+        v = np.empty(eng.n_states, np.float32)
+        eng.download(values=v)
+        res[mode] = bits(v).copy()
+        eng.close()
+    a, b = res.values()
+    np.testing.assert_array_equal(a, b)
