@@ -1,0 +1,186 @@
+// pair_sweep_src.cuh — CUDA source of the packed-pair evaluation sweep: the generic gather
+// sweep (policy_eval_kernel_4d/_6d of the reference, src/cuda_policy_iteration.py:616-649,
+// :1044-1079, + the max|x-y| reduction :563-571, :987-995) with TWO states per thread whose
+// weight trees and fma chains run as one packed mul.rn.f32x2 / fma.rn.f32x2 stream, compiled
+// at run time by NVRTC for sm_100a with the grid strides baked in as immediates.
+// build.py turns this file into the string pi::kPairSweepSrc; the host prepends
+//
+//   GP_D        grid dimensions (>= 3)
+//   GP_THREADS  threads per CTA (multiple of 32)      GP_MINB   CTAs per SM
+//   gp_off[]    V offset of corner c: sum of the storage strides of the set bits (bit d <-> dim d)
+//
+// Why.  The scalar sweep (pi::eval_sweep_kernel) spends 2^D scalar FMUL for the
+// leaf weights, 2^D-4 for the tree, 2^D FFMA for the chain and ~2^D IMAD for the gather
+// addresses per state — all on the FMA pipe, where a 3-register FFMA/FMUL/IMAD issues at half
+// rate on sm_100.  Here the two states of a thread share every FMA-pipe instruction (each
+// half of an f32x2 op rounds exactly like the scalar op, in the reference's order
+// w_c = ((((f_0 f_1) f_2) ..) f_{D-1}), ev = fma(w_c, V_c, ev), c ascending :602-613, :643-646,
+// :1030-1041, :1074-1076 => bit-identical V) and the gather addresses are base + immediate.
+// The gathers themselves stay scalar and fully general: nothing is assumed about the policy
+// or about which dimension is stored fastest.  Lane l of warp w owns states 64 w' + l and
+// 64 w' + 32 + l, so every gather instruction is still issued by 32 consecutive states
+// (same coalescing as the scalar sweep), rows are read from the engine's plain storage order.
+
+typedef unsigned long long gp_u64;
+
+struct GpCtl {   // == pi::Ctl
+    int base, parity0, done, conv_sweep;
+    float last_delta, check_delta;
+    unsigned long long changed;
+    unsigned int pad[8];
+};
+
+struct GpParams {
+    const unsigned char* rows;   // compacted rows of the policy, 16/8/4-byte planes (pi::Row<D>)
+    float* V0;
+    float* V1;
+    const GpCtl* ctl;
+    float* partial;              // [gridDim.x]
+    long long n_local;
+    long long n_pad;
+    long long s_begin;
+    float gamma;
+    int j;
+    int check;
+};
+
+#define GP_W (GP_D + 2)
+#define GP_N4 (GP_W / 4)
+#define GP_N2 ((GP_W % 4) / 2)
+#define GP_C (1 << GP_D)
+#define GP_H (GP_C / 2)
+
+__device__ __forceinline__ gp_u64 gp_pk(float a, float b) {
+    gp_u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void gp_unpk(gp_u64 v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ gp_u64 gp_mul2(gp_u64 a, gp_u64 b) {
+    gp_u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ gp_u64 gp_fma2(gp_u64 a, gp_u64 b, gp_u64 c) {
+    gp_u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float gp_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// row of local state s (streaming: read once, keep V in L1/L2)
+__device__ __forceinline__ void gp_load_row(const unsigned char* __restrict__ tab, long long n_pad, long long s,
+                                            unsigned (&w)[GP_W]) {
+#pragma unroll
+    for (int q = 0; q < GP_N4; ++q) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(tab + (size_t)q * 16u * (size_t)n_pad + (size_t)s * 16u));
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+#if GP_N2
+    {
+        uint2 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y)
+                     : "l"(tab + (size_t)GP_N4 * 16u * (size_t)n_pad + (size_t)s * 8u));
+        w[4 * GP_N4] = v.x; w[4 * GP_N4 + 1] = v.y;
+    }
+#endif
+#if GP_W % 2
+    {
+        unsigned v;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v)
+                     : "l"(tab + ((size_t)GP_N4 * 16u + (size_t)GP_N2 * 8u) * (size_t)n_pad + (size_t)s * 4u));
+        w[GP_W - 1] = v;
+    }
+#endif
+}
+
+extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const GpParams p)
+{
+    const GpCtl* __restrict__ ctl = p.ctl;
+    if (ctl->done) return;
+    const int par = (ctl->base + p.j + ctl->parity0) & 1;
+    const float* __restrict__ Vin = par ? p.V1 : p.V0;
+    float* __restrict__ Vout = par ? p.V0 : p.V1;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long sA = ((long long)blockIdx.x * (GP_THREADS / 32) + warp) * 64 + lane;
+    const long long sB = sA + 32;
+    const bool inA = sA < p.n_local, inB = sB < p.n_local;
+    float res = 0.0f;
+
+    if (inA) {
+        unsigned wA[GP_W], wB[GP_W];
+        gp_load_row(p.rows, p.n_pad, sA, wA);
+        if (inB) gp_load_row(p.rows, p.n_pad, sB, wB);
+        else {
+#pragma unroll
+            for (int k = 0; k < GP_W; ++k) wB[k] = k == 0 ? 0xfffffffeu : 0u;
+        }
+        const float voldA = Vin[p.s_begin + sA];
+        const float voldB = inB ? Vin[p.s_begin + sB] : 0.0f;
+        const int bA = (int)wA[0], bB = (int)wB[0];
+        // sentinel rows gather from a valid address and are discarded afterwards
+        const float* vA = Vin + (bA >= 0 ? bA : 0);
+        const float* vB = Vin + (bB >= 0 ? bB : 0);
+
+        // weight tree over dims 0..D-2, packed (state A, state B)
+        gp_u64 node[GP_H];
+        {
+            const float fa = __uint_as_float(wA[1]), fb = __uint_as_float(wB[1]);
+            node[0] = gp_pk(1.0f - fa, 1.0f - fb);
+            node[1] = gp_pk(fa, fb);
+#pragma unroll
+            for (int d = 1; d < GP_D - 1; ++d) {
+                const float xa = __uint_as_float(wA[1 + d]), xb = __uint_as_float(wB[1 + d]);
+                const gp_u64 f = gp_pk(xa, xb), g = gp_pk(1.0f - xa, 1.0f - xb);
+#pragma unroll
+                for (int c = GP_H / 2 - 1; c >= 0; --c) {   // constant trip count: node[] stays in registers
+                    if (c < (1 << d)) {
+                        const gp_u64 t = node[c];
+                        node[c + (1 << d)] = gp_mul2(t, f);
+                        node[c] = gp_mul2(t, g);
+                    }
+                }
+            }
+        }
+        const float la = __uint_as_float(wA[GP_D]), lb = __uint_as_float(wB[GP_D]);
+        const gp_u64 wl0 = gp_pk(1.0f - la, 1.0f - lb), wl1 = gp_pk(la, lb);
+
+        gp_u64 ev = gp_pk(0.0f, 0.0f);
+#pragma unroll
+        for (int c = 0; c < GP_C; ++c) {
+            const gp_u64 leaf = gp_mul2(node[c & (GP_H - 1)], (c & GP_H) ? wl1 : wl0);
+            ev = gp_fma2(leaf, gp_pk(__ldg(vA + gp_off[c]), __ldg(vB + gp_off[c])), ev);
+        }
+        float evA, evB;
+        gp_unpk(ev, evA, evB);
+        // sentinel rows: terminated (-1) -> sum := 0 (:231-232); absorbing (-2) -> new_V := V (:221)
+        const float vnewA = bA == -2 ? voldA : fmaf(p.gamma, bA >= 0 ? evA : 0.0f, __uint_as_float(wA[GP_D + 1]));
+        Vout[p.s_begin + sA] = vnewA;
+        res = fabsf(vnewA - voldA);
+        if (inB) {
+            const float vnewB = bB == -2 ? voldB : fmaf(p.gamma, bB >= 0 ? evB : 0.0f, __uint_as_float(wB[GP_D + 1]));
+            Vout[p.s_begin + sB] = vnewB;
+            res = fmaxf(res, fabsf(vnewB - voldB));
+        }
+    }
+    if (!p.check) return;
+    __shared__ float s_red[32];
+    res = gp_warp_max(res);
+    if (lane == 0) s_red[warp] = res;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float r = threadIdx.x < GP_THREADS / 32 ? s_red[threadIdx.x] : 0.0f;
+        r = gp_warp_max(r);
+        if (threadIdx.x == 0) p.partial[blockIdx.x] = r;
+    }
+}

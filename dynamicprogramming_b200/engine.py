@@ -383,6 +383,26 @@ class _CudaPolicyIterationBase(abc.ABC):
         return {"fast_dim": int(fast.value), "perm": [int(perm[k]) for k in range(D)],
                 "probe_lines": [float(lines[d]) for d in range(D)]}
 
+    def lookup_actions(self, states: np.ndarray) -> np.ndarray:
+        """Batched get_optimal_action (utils/barycentric.py:76-108) for `states` (n, D): on a live engine
+        the device-resident policy answers (pi_lookup_actions); after run() / load() the host `policy`
+        array is uploaded once into a lookup table (pi_lookup_create)."""
+        pts = np.ascontiguousarray(np.atleast_2d(states), dtype=np.float32)
+        if pts.shape[1] != self.N_DIMS:
+            raise ValueError(f"states must have {self.N_DIMS} columns, got {pts.shape}")
+        if getattr(self, "_engine", None):
+            out = np.empty(len(pts), dtype=np.float32)
+            _ffi.check(_ffi.lib().pi_lookup_actions(self._engine, _ffi.ptr(pts), len(pts), _ffi.ptr(out)))
+            return out
+        from .utils import PolicyLookup
+        look = getattr(self, "_lookup", None)
+        if look is None or look[0] is not self.policy:
+            if look is not None:
+                look[1].close()
+            look = (self.policy, PolicyLookup(self.policy, self.action_space, self.bounds_low, self.bounds_high, self.grid_shape))
+            self._lookup = look
+        return look[1](pts)
+
     def eval_kernel_info(self) -> dict:
         """Which evaluation-sweep kernel the build-time autotune selected (include/dpb200.h:
         pi_eval_kernel_info): the scalar gather sweep or the JIT-compiled x-line sweep."""
@@ -401,6 +421,13 @@ class _CudaPolicyIterationBase(abc.ABC):
                                              C.byref(mism), C.byref(wf), info))
         return {"ms_xline": ms_new.value, "ms_scalar": ms_base.value, "mismatches": int(mism.value),
                 "window_fraction": wf.value, "registers": int(info[0]), "grid": int(info[1]), "block": int(info[2])}
+
+    def debug_pair(self, threads: int = 256, minb: int = 2, iters: int = 5) -> dict:
+        """Test hook: packed-pair generic sweep vs the scalar sweep (bitwise comparison + timings)."""
+        ms_p, ms_s, mism, regs = C.c_float(), C.c_float(), C.c_int64(), C.c_int32()
+        _ffi.check(_ffi.lib().pi_debug_pair(self._engine, int(threads), int(minb), int(iters), C.byref(ms_p), C.byref(ms_s),
+                                            C.byref(mism), C.byref(regs)))
+        return {"ms_pair": ms_p.value, "ms_scalar": ms_s.value, "mismatches": int(mism.value), "registers": int(regs.value)}
 
     def to_internal_order(self, ref_array: np.ndarray) -> np.ndarray:
         """Reorder a reference-order (n_states,) array into the engine's storage order."""

@@ -1,0 +1,81 @@
+"""
+GPU counterpart of the reference's inference helpers (utils/barycentric.py):
+
+    get_optimal_action(state, policy, action_space, bounds_low, bounds_high,
+                       grid_shape, strides, corner_bits)            utils/barycentric.py:76-108
+
+The reference interpolates ONE state per call on the CPU (numba, single thread); here the
+policy table lives on the device and a call answers a whole batch of states with one CUDA
+thread each (libdpb200.so: pi_lookup_create / pi_lookup_query, include/dpb200.h).  The
+arithmetic of get_barycentric_weights_and_indices (:11-73) is reproduced as numba types it;
+the result of a query equals `lambdas @ action_space[policy[flat_indices]]` up to the
+summation order of the float32 dot product.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+class PolicyLookup:
+    """Device-resident policy table + batched `get_optimal_action`."""
+
+    def __init__(self, policy: np.ndarray, action_space: np.ndarray, bounds_low: np.ndarray, bounds_high: np.ndarray,
+                 grid_shape: np.ndarray, device: int = 0) -> None:
+        lib = _ffi.lib()
+        shape = [int(x) for x in np.asarray(grid_shape).ravel()]
+        self.n_dims = len(shape)
+        pol = np.ascontiguousarray(policy, dtype=np.int32).ravel()
+        if pol.size != int(np.prod(shape, dtype=np.int64)):
+            raise ValueError(f"policy has {pol.size} entries, grid_shape {shape} needs {int(np.prod(shape))}")
+        act = np.ascontiguousarray(action_space, dtype=np.float32).ravel()
+        grid = _ffi.PiGrid()
+        grid.n_dims = self.n_dims
+        for d in range(self.n_dims):
+            grid.shape[d] = shape[d]
+            grid.lo[d] = float(np.float32(bounds_low[d]))
+            grid.hi[d] = float(np.float32(bounds_high[d]))
+        handle = C.c_void_p()
+        _ffi.check(lib.pi_lookup_create(C.byref(grid), _ffi.ptr(pol), _ffi.ptr(act), len(act), int(device), C.byref(handle)))
+        self._h = handle
+
+    def __call__(self, states: np.ndarray) -> np.ndarray:
+        """states: (n, D) or (D,) float -> interpolated actions, (n,) float32."""
+        pts = np.ascontiguousarray(np.atleast_2d(states), dtype=np.float32)
+        if pts.shape[1] != self.n_dims:
+            raise ValueError(f"states must have {self.n_dims} columns, got {pts.shape}")
+        out = np.empty(len(pts), dtype=np.float32)
+        _ffi.check(_ffi.lib().pi_lookup_query(self._h, _ffi.ptr(pts), len(pts), _ffi.ptr(out)))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _ffi.lib().pi_lookup_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+_cache: dict = {}
+
+
+def get_optimal_action(state, policy, action_space, bounds_low, bounds_high, grid_shape, strides=None, corner_bits=None):
+    """Drop-in for utils.barycentric.get_optimal_action (same arguments; `strides` and `corner_bits`
+    are implied by `grid_shape` and accepted for compatibility).  Accepts one state or a batch; the
+    device table is cached per (policy, action_space) object pair."""
+    key = (id(policy), id(action_space))
+    hit = _cache.get(key)
+    if hit is None or hit[0] is not policy:
+        if len(_cache) >= 4:
+            _cache.pop(next(iter(_cache)))[1].close()
+        hit = (policy, PolicyLookup(policy, action_space, bounds_low, bounds_high, grid_shape))
+        _cache[key] = hit
+    out = hit[1](state)
+    return out[0] if np.ndim(state) == 1 else out

@@ -212,10 +212,29 @@ int pi_xline_compile_check(int32_t n_dims, int32_t bins, const char* cfg, int64_
 int pi_debug_xline(pi_engine* e, const char* cfg, int32_t iters, float* ms_xline, float* ms_scalar,
                    int64_t* mismatches, double* window_fraction, int32_t* info);
 
-/* N2 (next row): batched policy lookup with get_optimal_action semantics
- * (utils/barycentric.py:11-108; float64 arithmetic, corner_bits order).
+/* Test hook: the packed-pair generic sweep (csrc/pair_sweep_src.cuh: two states per thread,
+ * FMUL2/FFMA2, gather addresses as immediates; JIT) vs the scalar sweep; engine state unchanged.
+ * DPB200_PAIR = off (default) | auto | force | <threads>,<minb> controls the build-time selection. */
+int pi_debug_pair(pi_engine* e, int32_t threads, int32_t minb, int32_t iters, float* ms_pair, float* ms_scalar,
+                  int64_t* mismatches, int32_t* regs);
+
+/* N2: batched policy lookup with get_optimal_action semantics — action(p) = sum_c lambda_c(p) *
+ * action_space[policy[idx_c(p)]] (utils/barycentric.py:76-108; weights and indices as
+ * get_barycentric_weights_and_indices computes them, :11-73, in the arithmetic numba gives
+ * them: float32 step / cell, float64 t and weight products, corner_bits order).  One CUDA thread
+ * per query point; used by closed-loop rollouts (every runner's evaluate(), e.g.
+ * runners/pendulum_cuda.py:161-166) to query thousands of states per call.
  * points: n_points x n_dims float32 (host); out: n_points float32 (host). */
 int pi_lookup_actions(pi_engine* e, const float* points, int64_t n_points, float* out);
+
+/* The same lookup for a SAVED policy (Cls.load(path), src/cuda_policy_iteration.py:411-432;
+ * runners/hybrid_double_cartpole.py:35-43): the policy table (reference order, n_states int32)
+ * and the action values are uploaded once, queries are batched.  grid->axes is not used. */
+typedef struct pi_lookup pi_lookup;
+int pi_lookup_create(const pi_grid* grid, const int32_t* policy, const float* actions, int32_t n_actions,
+                     int32_t device, pi_lookup** out);
+int pi_lookup_query(pi_lookup* lookup, const float* points, int64_t n_points, float* out);
+void pi_lookup_destroy(pi_lookup* lookup);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,30 @@ def test_no_device_means_loud_failure_not_cpu_fallback():
     assert "no CPU fallback" in str(ei.value)
 
 
+def test_lookup_without_a_device_fails_loudly_too():
+    from dynamicprogramming_b200.utils import PolicyLookup
+
+    lib = _ffi.lib()
+    if lib.pi_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_ffi.EngineError) as ei:
+        PolicyLookup(np.zeros(4, np.int32), np.ones(2, np.float32), [0, 0], [1, 1], [2, 2])
+    assert ei.value.code == _ffi.PI_ERR_NO_DEVICE
+
+
+def test_jit_sweep_kernels_compile_for_sm_100a_without_a_gpu():
+    """The x-line sweep is compiled per grid at run time; the same NVRTC path is checked here on
+    synthetic grids (every K / LV / roll variant the engine can select)."""
+    lib = _ffi.lib()
+    n = __import__("ctypes").c_int64()
+    for D, bins, cfg in [(6, 20, b"4,0,4,8,1,1:1,1,1,4,10"), (6, 20, b"2,0,4,8,2,1:1,1,1,2,10"), (6, 8, b"2,1,2,4,2,4:1,1,1,2,4"),
+                         (4, 40, b"4,0,4,8,1,2:1,2,4"), (4, 12, b"2,1,2,8,2,2:1,3,6"), (3, 20, b"4,0,2,8,1,1:4,4")]:
+        assert lib.pi_xline_compile_check(D, bins, cfg, __import__("ctypes").byref(n)) == _ffi.PI_OK, lib.pi_last_error()
+        assert n.value > 10_000
+    assert lib.pi_xline_compile_check(6, 21, b"4,0,4,8,1,1:1,1,1,1,3", None) == _ffi.PI_ERR_INVALID   # 21 % 4 != 0
+    assert lib.pi_xline_compile_check(2, 20, b"4,0,4,8,1,1:4", None) == _ffi.PI_ERR_INVALID
+
+
 def test_wrong_number_of_dimensions_asserts_like_the_reference():
     spec = envs.REGISTRY["pendulum"]
     bins = {"a": np.linspace(0, 1, 4, dtype=np.float32)}

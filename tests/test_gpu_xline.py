@@ -106,3 +106,38 @@ def test_upload_policy_refreshes_the_tile_ordered_rows(monkeypatch):
         eng.close()
     a, b = res.values()
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("env,bins", [("double_cartpole_swingup", 8), ("cartpole_swingup", 16), ("double_pendulum_swingup", 13),
+                                      ("overhead_crane", 11)])
+def test_packed_pair_sweep_is_bit_identical_to_the_scalar_sweep(env, bins, monkeypatch):
+    """csrc/pair_sweep_src.cuh (two states per thread, FMUL2/FFMA2, immediate gather offsets; any storage order,
+    odd sizes) against pi::eval_sweep_kernel, then a full run with it forced on against the reference kernels."""
+    monkeypatch.setenv("DPB200_XLINE", "off")
+    monkeypatch.setenv("DPB200_PAIR", "off")
+    eng = envs.make(env, bins=bins)
+    eng.build_table()
+    eng.sweeps(20)
+    eng.policy_improvement()
+    eng.sweeps(5)
+    for threads, minb in ((64, 8), (256, 2)):
+        out = eng.debug_pair(threads, minb, iters=1)
+        assert out["mismatches"] == 0, out
+    eng.close()
+
+
+def test_full_policy_iteration_with_the_packed_pair_sweep_matches_the_reference(monkeypatch, ref_runner):
+    monkeypatch.setenv("DPB200_XLINE", "off")
+    monkeypatch.setenv("DPB200_PAIR", "force")
+    spec = envs.REGISTRY["double_cartpole"]
+    c = spec.config()
+    c.max_pi_iter, c.max_eval_iter = 3, 200
+    eng = spec.make(bins=7, config=c)
+    eng.build_table()
+    assert "gp_sweep" in eng.eval_kernel_info()["kernel"]
+    ref = ref_runner.from_engine_env("double_cartpole", bins=7, config=c)
+    eng.run()
+    ref.run()
+    assert eng.total_eval_sweeps == ref.total_sweeps and eng.pi_iterations == ref.pi_iterations
+    np.testing.assert_array_equal(eng.policy, ref.policy)
+    np.testing.assert_array_equal(bits(eng.value_function), bits(ref.value_function))
