@@ -38,6 +38,9 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# stdout carries exactly ONE JSON line: NCCL's own messages (e.g. "NCCL version ..." when the box sets
+# NCCL_DEBUG) go to stderr instead of stdout
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ENV = "double_cartpole_swingup"
 SWEEPS_PER_STEP = 25

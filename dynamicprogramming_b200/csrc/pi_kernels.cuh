@@ -247,6 +247,12 @@ __device__ __forceinline__ float warp_max(float v) {
 // counters: [0] pairs, [1] regular pairs, [2] quads, [3] regular quads.
 __device__ __forceinline__ void count_regular_groups(int base, bool in, unsigned long long* counters) {
     if (counters == nullptr) return;
+    // Only the FRACTION matters: on large grids every 4th block is counted, reduced in shared memory,
+    // and adds 4 global atomics (an atomic per warp cost 8 ms on K5: 8 M same-address atomics).
+    if (gridDim.x > 1024 && (blockIdx.x & 3) != 0) return;
+    __shared__ unsigned s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool live = base >= 0;
@@ -264,10 +270,12 @@ __device__ __forceinline__ void count_regular_groups(int base, bool in, unsigned
         const unsigned heads = __ballot_sync(full, in && j == 0);
         const unsigned regs = __ballot_sync(full, in && j == 0 && regular);
         if (lane == 0 && heads) {
-            atomicAdd(counters + (K - 2), (unsigned long long)__popc(heads));
-            atomicAdd(counters + (K - 1), (unsigned long long)__popc(regs));
+            atomicAdd(&s_cnt[K - 2], (unsigned)__popc(heads));
+            atomicAdd(&s_cnt[K - 1], (unsigned)__popc(regs));
         }
     }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------

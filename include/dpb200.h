@@ -205,7 +205,8 @@ int pi_get_stats(const pi_engine* e, pi_stats* stats);
  * DPB200_XLINE = off | auto | [force:]K,LV,PF,warps,minb[,roll]:T0,T1,..[;more] overrides.
  * pi_eval_kernel_info returns 1 (x-line) / 0 (scalar), a description and the probe timings. */
 int pi_eval_kernel_info(const pi_engine* e, char* buf, int32_t buf_len, double* ms_scalar, double* ms_selected);
-/* Compile-only check of the x-line sweep for a synthetic bins^n_dims grid; needs no GPU. */
+/* Compile-only check of a JIT sweep for a synthetic bins^n_dims grid; needs no GPU.
+ * cfg: an x-line configuration, or "pair:<threads>,<minb>" for the packed-pair sweep. */
 int pi_xline_compile_check(int32_t n_dims, int32_t bins, const char* cfg, int64_t* cubin_bytes);
 /* Test hook: x-line sweep `cfg` vs the scalar sweep on the current rows and V (bitwise
  * comparison + timings); info = {registers, grid, block, tiles}; engine state unchanged. */

@@ -23,19 +23,32 @@ world = int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 td = pdist.init_process_group()
-cases = [("cartpole", 12, 4), ("mountain_car", 60, None), ("double_pendulum_swingup", 10, 3),
-         ("double_cartpole_swingup", 7, 2), ("pendulum", 33, 6)]
+# (env, bins, max_pi_iter, engine environment of the SHARDED run); the 1-GPU comparison run always uses the
+# scalar sweep, so the x-line cases also prove: sharded x-line sweep == unsharded scalar sweep, bit for bit
+XL = {"DPB200_FAST_DIM": "0", "DPB200_XLINE": "force:2,0,4,8,2,1:1,1,1,8,8"}
+XL4 = {"DPB200_FAST_DIM": "0", "DPB200_XLINE": "force:4,0,4,8,1,1:1,6,12"}
+cases = [("cartpole", 12, 4, {}), ("mountain_car", 60, None, {}), ("double_pendulum_swingup", 10, 3, {}),
+         ("double_cartpole_swingup", 7, 2, {}), ("pendulum", 33, 6, {}),
+         ("double_cartpole_swingup", 8, 2, XL), ("cartpole_swingup", 12, 3, XL4)]
 ok = True
-for env, bins, max_pi in cases:
+for env, bins, max_pi, engine_env in cases:
+    for k in ("DPB200_FAST_DIM", "DPB200_XLINE"):
+        os.environ.pop(k, None)
+    os.environ.update(engine_env)
     spec = envs.REGISTRY[env]
     cfg = spec.config()
     if max_pi:
         cfg.max_pi_iter = max_pi
     shard = pdist.make_shard(local)
     eng = spec.make(bins=bins, config=cfg, device=local, shard=shard)
+    eng.build_table()
+    kernel = eng.eval_kernel_info()["kernel"]
+    if engine_env:
+        assert "xl_sweep" in kernel, kernel
     eng.run()
-    res = dict(env=env, bins=bins, N=eng.n_states, pi=eng.pi_iterations, sweeps=eng.total_eval_sweeps)
+    res = dict(env=env, bins=bins, N=eng.n_states, pi=eng.pi_iterations, sweeps=eng.total_eval_sweeps, kernel=kernel[:40])
     if rank == 0:
+        os.environ["DPB200_XLINE"] = "off"
         one = spec.make(bins=bins, config=cfg, device=local)
         one.run()
         res.update(pi_1gpu=one.pi_iterations, sweeps_1gpu=one.total_eval_sweeps,

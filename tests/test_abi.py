@@ -105,6 +105,7 @@ def test_jit_sweep_kernels_compile_for_sm_100a_without_a_gpu():
                          (4, 40, b"4,0,4,8,1,2:1,2,4"), (4, 12, b"2,1,2,8,2,2:1,3,6"), (3, 20, b"4,0,2,8,1,1:4,4")]:
         assert lib.pi_xline_compile_check(D, bins, cfg, __import__("ctypes").byref(n)) == _ffi.PI_OK, lib.pi_last_error()
         assert n.value > 10_000
+    assert lib.pi_xline_compile_check(6, 20, b"pair:64,8", None) == _ffi.PI_OK
     assert lib.pi_xline_compile_check(6, 21, b"4,0,4,8,1,1:1,1,1,1,3", None) == _ffi.PI_ERR_INVALID   # 21 % 4 != 0
     assert lib.pi_xline_compile_check(2, 20, b"4,0,4,8,1,1:4", None) == _ffi.PI_ERR_INVALID
 
