@@ -225,7 +225,9 @@ def run_ours(args) -> dict:
             "config": {"workload": f"{ENV} 6-D --bins {args.bins} ({N:,} states x {eng.n_actions} actions), "
                                    f"policy evaluation, step = {SWEEPS_PER_STEP} Jacobi sweeps (one reference sync interval)",
                        "policy": "greedy policy after PI iteration 1", "gamma": eng.config.gamma,
-                       "sharding": "contiguous state ranges, needs-driven V exchange (NCCL)" if world > 1 else "single GPU",
+                       "sharding": ("contiguous state ranges, needs-driven V exchange: " + os.environ.get("DPB200_EXCHANGE", "p2p") +
+                                    " (p2p = peer stores fused into the sweep kernel over CUDA IPC / NVLink + barrier kernel; nccl = grouped send/recv)")
+                       if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (rows %.2f GB + V %.2f GB per sweep)" % (
                            (D + 2) * 4 * N / 1e9, 4 * N / 1e9)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 4),
@@ -370,7 +372,17 @@ def main() -> int:
     ap.add_argument("--no-converge", action="store_true")
     args = ap.parse_args()
     _quiet_logs()
-    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    # stdout carries exactly ONE JSON line: while the benchmark runs, file descriptor 1 points at stderr, so
+    # anything a library prints there (torch's "NCCL version ..." banner under torchrun) cannot precede it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if out is not None:
         print(json.dumps(out), flush=True)
     return 0

@@ -30,6 +30,22 @@ struct GpCtl {   // == pi::Ctl
     unsigned int pad[8];
 };
 
+
+// == pi::PeerOut (pi_kernels.cuh): sharded runs store new values straight into the V buffers of the
+// ranks that need them (CUDA IPC peer pointers over NVLink); n == 0 otherwise.
+struct GpPeerOut {
+    int n;
+    int pad;
+    float* V0[7];
+    float* V1[7];
+    long long lo[7];
+    long long hi[7];
+};
+__device__ __forceinline__ void gp_store_peers(const GpPeerOut& po, bool out_is_V0, long long g, float v) {
+    for (int r = 0; r < po.n; ++r)
+        if (g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
+}
+
 struct GpParams {
     const unsigned char* rows;   // compacted rows of the policy, 16/8/4-byte planes (pi::Row<D>)
     float* V0;
@@ -42,6 +58,7 @@ struct GpParams {
     float gamma;
     int j;
     int check;
+    GpPeerOut peers;
 };
 
 #define GP_W (GP_D + 2)
@@ -166,10 +183,12 @@ extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const
         // sentinel rows: terminated (-1) -> sum := 0 (:231-232); absorbing (-2) -> new_V := V (:221)
         const float vnewA = bA == -2 ? voldA : fmaf(p.gamma, bA >= 0 ? evA : 0.0f, __uint_as_float(wA[GP_D + 1]));
         Vout[p.s_begin + sA] = vnewA;
+        if (p.peers.n) gp_store_peers(p.peers, par != 0, p.s_begin + sA, vnewA);
         res = fabsf(vnewA - voldA);
         if (inB) {
             const float vnewB = bB == -2 ? voldB : fmaf(p.gamma, bB >= 0 ? evB : 0.0f, __uint_as_float(wB[GP_D + 1]));
             Vout[p.s_begin + sB] = vnewB;
+            if (p.peers.n) gp_store_peers(p.peers, par != 0, p.s_begin + sB, vnewB);
             res = fmaxf(res, fabsf(vnewB - voldB));
         }
     }

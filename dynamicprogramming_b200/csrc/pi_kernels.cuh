@@ -80,6 +80,61 @@ __host__ __device__ inline long long ref_to_internal(const GridDesc& g, long lon
 }
 
 // ---------------------------------------------------------------------------
+// Sharded runs: fused V exchange.  Every evaluation-sweep kernel stores a new value not only into
+// its own V buffer but also, through peer pointers (CUDA IPC over NVLink / NVSwitch), directly into
+// the V buffer of every rank whose transition rows reference that state (`[lo, hi)` = the sub-range
+// of THIS rank's slice that peer r needs, computed once after the table build).  The transfer
+// overlaps the sweep tile by tile; a sweep ends with xgpu_barrier_kernel instead of an NCCL
+// send/recv group.  Replaces nothing in the reference (single GPU); SURVEY §5 / §8(e).
+// ---------------------------------------------------------------------------
+constexpr int kMaxPeers = 7;
+struct PeerOut {
+    int n;
+    int pad;
+    float* V0[kMaxPeers];
+    float* V1[kMaxPeers];
+    long long lo[kMaxPeers];
+    long long hi[kMaxPeers];
+};
+
+// out_is_V0: the sweep writes buffer 0 (of every rank) this time
+__device__ __forceinline__ void store_peers(const PeerOut& po, bool out_is_V0, long long g, float v) {
+    for (int r = 0; r < po.n; ++r)
+        if (g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
+}
+
+// Cross-GPU barrier at the end of a sweep: thread t publishes this rank's epoch into rank t's flag
+// array (release, system scope — the sweep kernel before it in stream order has completed, so its
+// peer stores are performed), then waits until rank t's epoch has arrived in the local array.
+// flags_local[r] is written only by rank r.  A rank that never arrives (crashed peer) trips the
+// timeout instead of hanging the GPU; the host turns err != 0 into PI_ERR_COMM.
+struct BarrierParams {
+    unsigned* flags_local;
+    unsigned* flags_peer[kMaxPeers + 1];   // indexed by rank; [own rank] unused
+    unsigned* epoch;                       // local sweep counter
+    unsigned* err;
+    int rank;
+    int world;
+};
+__global__ void xgpu_barrier_kernel(const BarrierParams b) {
+    const int t = threadIdx.x;
+    const unsigned e = *b.epoch + 1;
+    if (t < b.world && t != b.rank) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags_peer[t] + b.rank), "r"(e) : "memory");
+        const long long t0 = clock64();
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(b.flags_local + t) : "memory");
+            if ((int)(seen - e) >= 0) break;
+            if (clock64() - t0 > 6000000000LL) { *b.err = 1u; break; }   // ~3 s at 2 GHz
+        } while (true);
+    }
+    __syncthreads();
+    if (t == 0) *b.epoch = e;
+}
+
+// ---------------------------------------------------------------------------
 // Row layout helpers
 // ---------------------------------------------------------------------------
 template <int D>
@@ -300,6 +355,7 @@ struct EvalParams {
     int check;  // 1 if the host will examine the residual of this sweep (sync point, :325)
     int lookahead;  // blocks ahead whose rows are prefetched into L2 (0 = off)
     int stride[kMaxDims];
+    PeerOut peers;  // sharded runs with the fused exchange: where else new values go (n = 0: nowhere)
 };
 
 // TMA bulk prefetch of `bytes` (multiple of 16) starting at p into L2.
@@ -358,6 +414,7 @@ __global__ void __launch_bounds__(kBlock) eval_sweep_kernel(const EvalParams p) 
             vnew = fmaf(p.gamma, ev, __uint_as_float(w[D + 1]));  // reward + gamma*ev contracts to one FMA
         }
         Vout[p.s_begin + s] = vnew;
+        if (p.peers.n) store_peers(p.peers, par != 0, p.s_begin + s, vnew);
         res = fabsf(vnew - vold);
     }
     if (!p.check) return;  // the reference reads the residual only at sync points (:325-326)
@@ -571,6 +628,10 @@ __global__ void __launch_bounds__(kBlock) eval_sweep_pair_kernel(const EvalParam
         } else {
             Vout[g0] = vnew0;
             if (has1) Vout[g0 + 1] = vnew1;
+        }
+        if (p.peers.n) {
+            store_peers(p.peers, par != 0, g0, vnew0);
+            if (has1) store_peers(p.peers, par != 0, g0 + 1, vnew1);
         }
         res = fabsf(vnew0 - vold0);
         if (has1) res = fmaxf(res, fabsf(vnew1 - vold1));

@@ -41,6 +41,22 @@ struct XlCtl {   // == pi::Ctl
     unsigned int pad[8];
 };
 
+
+// == pi::PeerOut (pi_kernels.cuh): sharded runs store new values straight into the V buffers of the
+// ranks that need them (CUDA IPC peer pointers over NVLink); n == 0 otherwise.
+struct XlPeerOut {
+    int n;
+    int pad;
+    float* V0[7];
+    float* V1[7];
+    long long lo[7];
+    long long hi[7];
+};
+__device__ __forceinline__ void xl_store_peers(const XlPeerOut& po, bool out_is_V0, long long g, float v) {
+    for (int r = 0; r < po.n; ++r)
+        if (g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
+}
+
 struct XlParams {
     const unsigned* rows;      // plane w (word w of every row) at rows + w * plane_words
     long long plane_words;
@@ -55,6 +71,7 @@ struct XlParams {
     int j;
     int check;
     int prefetch;              // 1: TMA-prefetch the next tile's rows into L2
+    XlPeerOut peers;
 };
 
 #define XL_W (XL_D + 2)
@@ -423,6 +440,10 @@ extern "C" __global__ void __launch_bounds__(XL_WARPS * 32, XL_MINB) xl_sweep(co
 #else
             *reinterpret_cast<float2*>(Vout + v0) = make_float2(vnew[0], vnew[1]);
 #endif
+            if (p.peers.n) {
+#pragma unroll
+                for (int j = 0; j < XL_K; ++j) xl_store_peers(p.peers, par != 0, v0 + j, vnew[j]);
+            }
         }
     }
 
