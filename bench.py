@@ -185,14 +185,13 @@ def run_ours(args) -> dict:
 
     # ---- end-to-end arm: host buffers in, host buffers out ---------------------
     n_local = hi - lo
-    pol_host = torch.empty(N, dtype=torch.int32).pin_memory()
+    pol_host = torch.empty(n_local, dtype=torch.int32).pin_memory()
     v_host = torch.empty(n_local, dtype=torch.float32).pin_memory()
-    _, p0 = eng.download()
-    pol_host.numpy()[:] = p0
     pol_np, v_np = pol_host.numpy(), v_host.numpy()
+    _ffi.check(lib.pi_copy_local_results(eng._engine, None, _ffi.ptr(pol_np)))      # this rank's slice, storage order
 
     def e2e_step():
-        _ffi.check(lib.pi_upload_policy(eng._engine, _ffi.ptr(pol_np)))         # H2D policy slice + row compaction
+        _ffi.check(lib.pi_upload_policy_local(eng._engine, _ffi.ptr(pol_np)))     # H2D policy slice + row compaction
         d, _ = eng.sweeps(SWEEPS_PER_STEP)
         _ffi.check(lib.pi_copy_local_results(eng._engine, _ffi.ptr(v_np), None))  # D2H value slice
         return d
@@ -232,7 +231,7 @@ def run_ours(args) -> dict:
                            (D + 2) * 4 * N / 1e9, 4 * N / 1e9)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 4),
                     "d2h_bytes_per_step": int(n_local * 4 + 4),
-                    "call": "pi_upload_policy + pi_sweeps(25) + pi_copy_local_results (pinned host buffers)"},
+                    "call": "pi_upload_policy_local + pi_sweeps(25) + pi_copy_local_results (pinned host buffers, each rank its own slice)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

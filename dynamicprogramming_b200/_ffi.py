@@ -91,6 +91,7 @@ SIGNATURES = {
     "pi_copy_local_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pi_upload_policy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pi_upload_values": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pi_upload_policy_local": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pi_sweeps": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pi_expand_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),

@@ -119,6 +119,7 @@ struct BarrierParams {
 __global__ void xgpu_barrier_kernel(const BarrierParams b) {
     const int t = threadIdx.x;
     const unsigned e = *b.epoch + 1;
+    if (*b.err) return;   // a barrier already timed out: do not wait again, the host reports PI_ERR_COMM
     if (t < b.world && t != b.rank) {
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags_peer[t] + b.rank), "r"(e) : "memory");
@@ -127,7 +128,7 @@ __global__ void xgpu_barrier_kernel(const BarrierParams b) {
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(b.flags_local + t) : "memory");
             if ((int)(seen - e) >= 0) break;
-            if (clock64() - t0 > 6000000000LL) { *b.err = 1u; break; }   // ~3 s at 2 GHz
+            if (clock64() - t0 > 20000000000LL) { *b.err = 1u; break; }   // ~10 s at 2 GHz
         } while (true);
     }
     __syncthreads();

@@ -350,6 +350,12 @@ class _CudaPolicyIterationBase(abc.ABC):
         assert p.shape == (self.n_states,)
         _ffi.check(_ffi.lib().pi_upload_policy(self._engine, _ffi.ptr(p)))
 
+    def upload_policy_local(self, policy_local: np.ndarray) -> None:
+        """This rank's slice of the policy in the engine's storage order (see `to_internal_order`,
+        `pi_copy_local_results`): no full-grid staging, no collective."""
+        p = np.ascontiguousarray(policy_local, dtype=np.int32)
+        _ffi.check(_ffi.lib().pi_upload_policy_local(self._engine, _ffi.ptr(p)))
+
     def upload_values(self, values: np.ndarray) -> None:
         v = np.ascontiguousarray(values, dtype=np.float32)
         assert v.shape == (self.n_states,)

@@ -158,6 +158,9 @@ int pi_copy_local_results(pi_engine* e, float* value_function_local, int32_t* po
 /* Host <-> device hand-off used by the end-to-end evaluation call and tests. */
 int pi_upload_policy(pi_engine* e, const int32_t* policy);     /* n_states  */
 int pi_upload_values(pi_engine* e, const float* value_function); /* n_states */
+/* This rank's slice of the policy only, in the engine's storage order (the layout
+ * pi_copy_local_results returns): n_local int32; no collective, no full-grid staging. */
+int pi_upload_policy_local(pi_engine* e, const int32_t* policy_local);
 
 /* Exactly `n_sweeps` evaluation sweeps with no convergence test (steady-state
  * timing); *delta = residual of the last sweep, *device_ms = CUDA-event time. */

@@ -201,3 +201,26 @@ def test_storage_order_never_changes_results(fast, ref_runner, monkeypatch):
     assert eng.total_eval_sweeps == ref.total_sweeps
     np.testing.assert_array_equal(eng.policy, ref.policy)
     np.testing.assert_array_equal(bits(eng.value_function), bits(ref.value_function))
+
+
+def test_local_policy_upload_equals_the_full_upload():
+    """pi_upload_policy_local (storage order, this rank's slice) == pi_upload_policy (reference order, whole grid)."""
+    res = []
+    rng = np.random.default_rng(3)
+    P = None
+    for local in (False, True):
+        eng = envs.make("cartpole_swingup", bins=9)
+        eng.build_table()
+        if P is None:
+            P = rng.integers(0, eng.n_actions, eng.n_states).astype(np.int32)
+        if local:
+            eng.upload_policy_local(eng.to_internal_order(P))
+        else:
+            eng.upload_policy(P)
+        eng.sweeps(4)
+        v, p = eng.download()
+        res.append((bits(v).copy(), p.copy()))
+        eng.close()
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][1], P)
