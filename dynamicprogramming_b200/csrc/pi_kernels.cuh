@@ -848,7 +848,10 @@ __global__ void expand_rows_kernel(const unsigned char* table, long long n_pad, 
 __global__ void fill_masked_kernel(GridDesc g, float* V0, float* V1, const unsigned char* mask_ref, long long n,
                                    float value) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && mask_ref[internal_to_ref(g, i)]) { V0[i] = value; V1[i] = value; }
+    if (i < n && mask_ref[internal_to_ref(g, i)]) {
+        if (V0) V0[i] = value;
+        if (V1) V1[i] = value;
+    }
 }
 
 // out[k] = ref_full[ref index of internal state s_begin + k]   (reference order -> internal slice)

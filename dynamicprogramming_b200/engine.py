@@ -63,8 +63,23 @@ class DeviceArray:
     reference object).  Exposes __cuda_array_interface__ so torch / cupy can
     wrap it zero-copy: ``torch.as_tensor(pi.d_value_function, device="cuda")``."""
 
-    def __init__(self, ptr: int, shape: tuple, typestr: str, owner) -> None:
-        self._ptr, self.shape, self._typestr, self._owner = ptr, shape, typestr, owner
+    def __init__(self, ptr: int, shape: tuple, typestr: str, owner, role: int | None = None) -> None:
+        self._ptr, self.shape, self._typestr, self._owner, self._role = ptr, shape, typestr, owner, role
+
+    def __setitem__(self, key, value) -> None:
+        """``d_value_function[mask] = scalar`` with a boolean mask over the whole grid in reference
+        order — the store a reference subclass does on its cupy arrays
+        (runners/overhead_crane_cuda.py:199-202).  The buffer itself is in the engine's storage
+        order, so the store goes through pi_set_values_buffer rather than raw indexing."""
+        if self._role is None:
+            raise TypeError("this device buffer is read-only from Python")
+        if hasattr(key, "get"):          # a cupy array
+            key = key.get()
+        mask = np.asarray(key)
+        if mask.dtype != np.bool_ or mask.shape != (self._owner.n_states,):
+            raise TypeError("only boolean-mask stores over the whole grid (n_states,) are supported")
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        _ffi.check(_ffi.lib().pi_set_values_buffer(self._owner._engine, self._role, _ffi.ptr(m), float(value)))
 
     @property
     def __cuda_array_interface__(self) -> dict:
@@ -216,8 +231,8 @@ class _CudaPolicyIterationBase(abc.ABC):
         v, nv, pol, term = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         _ffi.check(lib.pi_device_ptrs(self._engine, C.byref(v), C.byref(nv), C.byref(pol), C.byref(term)))
         n_local = lib.pi_local_end(self._engine) - lib.pi_local_begin(self._engine)
-        self.d_value_function = DeviceArray(v.value, (self.n_states,), "<f4", self)
-        self.d_new_value_function = DeviceArray(nv.value, (self.n_states,), "<f4", self)
+        self.d_value_function = DeviceArray(v.value, (self.n_states,), "<f4", self, role=0)
+        self.d_new_value_function = DeviceArray(nv.value, (self.n_states,), "<f4", self, role=1)
         self.d_policy = DeviceArray(pol.value, (n_local,), "<i4", self)
         self.d_terminal_mask = DeviceArray(term.value, (n_local,), "|u1", self)
 

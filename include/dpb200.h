@@ -127,6 +127,11 @@ int pi_set_terminal(pi_engine* e, const uint8_t* mask, float value);
  * overhead-crane goal initialisation (runners/overhead_crane_cuda.py:193-206). */
 int pi_set_values(pi_engine* e, const uint8_t* mask, float value);
 
+/* The same on ONE buffer: which = 0 -> d_value_function, 1 -> d_new_value_function.  What a
+ * boolean-mask store `self.d_value_function[d_mask] = value` of a reference subclass does
+ * (runners/overhead_crane_cuda.py:201-202); `mask` is in reference order, n_states bytes. */
+int pi_set_values_buffer(pi_engine* e, int32_t which, const uint8_t* mask, float value);
+
 /* Transition-table build (new stage; arithmetic oracle = step_dynamics +
  * get_barycentric_{2,4,6}d, src/cuda_policy_iteration.py:183-210, :580-614,
  * :1007-1042).  One compact row per (state, action): base flat index,
