@@ -348,6 +348,16 @@ def run_reference(args) -> dict | None:
         torch.cuda.synchronize()
         ms_per_step = e0.elapsed_time(e1) / args.steps
         value = N * SWEEPS_PER_STEP / (ms_per_step * 1e-3)
+        # K1 (pendulum --bins 200) to the end with the reference's kernels and host loop, like our arm's
+        # time_to_converge: run() only (kernels are already compiled on both sides), D2H included
+        ttc = None
+        if not args.no_converge:
+            ref1 = ref_runner.from_engine_env("pendulum")
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref1.run()
+            ttc = {"workload": "pendulum 2-D --bins 200 (40,000 states x 21 actions), reference kernels + reference host loop, run() incl. D2H",
+                   "seconds": time.perf_counter() - t0, "pi_iterations": ref1.pi_iterations, "eval_sweeps": ref1.total_sweeps}
         kind = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                 "sample": "the reference's own eval kernel + max|x-y| reduction (oracle/_ref cubin, NVRTC-compiled "
                           "from /root/reference) on one B200, full grid; the reference has no CPU path"}
@@ -356,10 +366,14 @@ def run_reference(args) -> dict | None:
         value = cb["value"]
         ms_per_step = N * SWEEPS_PER_STEP / value * 1e3
         kind = dict(cb)
-    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        ttc = None
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc, "cpu_baseline": kind,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if ttc is not None:
+        out["time_to_converge"] = ttc
+    return out
 
 
 def main() -> int:

@@ -131,8 +131,12 @@ class _CudaPolicyIterationBase(abc.ABC):
         """(n_states, D) float32, row-major, dim 0 slowest — materialised on first use
         (the reference builds it eagerly with meshgrid(indexing="ij") + column_stack)."""
         if self._states_space is None:
-            grids = np.meshgrid(*self._axes, indexing="ij")
-            self._states_space = np.column_stack([g.ravel() for g in grids]).astype(np.float32)
+            if getattr(self, "_axes", None) is not None:
+                grids = np.meshgrid(*self._axes, indexing="ij")
+                self._states_space = np.column_stack([g.ravel() for g in grids]).astype(np.float32)
+            else:   # an instance made by load(): read the entry now
+                with np.load(self._states_file) as data:
+                    self._states_space = data["states_space"]
         return self._states_space
 
     @states_space.setter
@@ -318,10 +322,13 @@ class _CudaPolicyIterationBase(abc.ABC):
     # ── Persistence: the reference's nine-array .npz (:392-432) ───────────────
 
     def save(self, filepath: Path | str) -> None:
+        """The reference's nine-array uncompressed .npz (:392-409), same keys, dtypes, shapes and order.
+        `states_space` (N x D float32: 1.5 GB at 6-D / 20 bins) is the only large entry; when it has
+        never been materialised it is STREAMED into the archive slab by slab along dim 0
+        — the file np.load sees is the one np.savez would have written."""
         filepath = Path(filepath).with_suffix(".npz")
         filepath.parent.mkdir(parents=True, exist_ok=True)
-        np.savez(
-            filepath,
+        small = dict(
             value_function=self.value_function,
             policy=self.policy,
             bounds_low=self.bounds_low,
@@ -330,18 +337,50 @@ class _CudaPolicyIterationBase(abc.ABC):
             strides=self.strides,
             corner_bits=self.corner_bits,
             action_space=self.action_space,
-            states_space=self.states_space,
         )
+        if self._states_space is not None or getattr(self, "_axes", None) is None:
+            np.savez(filepath, **small, states_space=self.states_space)
+        else:
+            self._save_streamed(filepath, small)
         logger.success(f"Policy saved to {filepath.resolve()}")
+
+    def _save_streamed(self, filepath: Path, small: dict) -> None:
+        import zipfile
+
+        from numpy.lib import format as npy_format
+
+        D = self.N_DIMS
+        inner = self.n_states // len(self._axes[0])
+        with zipfile.ZipFile(filepath, mode="w", compression=zipfile.ZIP_STORED, allowZip64=True) as zf:
+            for key, val in small.items():
+                with zf.open(key + ".npy", "w", force_zip64=True) as fid:
+                    npy_format.write_array(fid, np.asanyarray(val), allow_pickle=False)
+            with zf.open("states_space.npy", "w", force_zip64=True) as fid:
+                header = {"descr": npy_format.dtype_to_descr(np.dtype(np.float32)), "fortran_order": False,
+                          "shape": (self.n_states, D)}
+                npy_format.write_array_header_1_0(fid, header)
+                if D == 1:
+                    fid.write(np.ascontiguousarray(self._axes[0], np.float32).reshape(-1, 1).tobytes())
+                else:
+                    rest = np.meshgrid(*self._axes[1:], indexing="ij")
+                    slab = np.empty((inner, D), dtype=np.float32)
+                    for d, g in enumerate(rest):
+                        slab[:, d + 1] = g.ravel()
+                    del rest
+                    for x0 in self._axes[0]:
+                        slab[:, 0] = x0
+                        fid.write(memoryview(slab).cast("B"))
 
     @classmethod
     def load(cls, filepath: Path | str):
-        """Load a saved policy (no GPU required)."""
+        """Load a saved policy (no GPU required).  `states_space` is read from the archive on first
+        use (np.load is lazy per key), everything else eagerly as the reference does (:411-432)."""
         filepath = Path(filepath).with_suffix(".npz")
         data = np.load(filepath)
         instance = cls.__new__(cls)
         instance._engine = None
         instance._states_space = None
+        instance._states_file = filepath
         instance.value_function = data["value_function"]
         instance.policy = data["policy"]
         instance.bounds_low = data["bounds_low"]
@@ -350,10 +389,12 @@ class _CudaPolicyIterationBase(abc.ABC):
         instance.strides = data["strides"]
         instance.corner_bits = data["corner_bits"]
         instance.action_space = data["action_space"]
-        instance.states_space = data["states_space"]
+        if "states_space" not in data.files:
+            raise KeyError("states_space is not a file in the archive")
         instance.n_actions = len(instance.action_space)
-        instance.n_states = len(instance.states_space)
+        instance.n_states = len(instance.policy)
         instance.config = CudaPIConfig()
+        data.close()
         logger.success(f"Policy loaded from {filepath.resolve()}")
         return instance
 

@@ -118,3 +118,31 @@ def test_duplicate_axis_nodes_are_rejected():
     inst.n_states, inst.n_actions = 9, 1
     with pytest.raises(ValueError):
         inst._precompute_grid_metadata()
+
+
+def test_streamed_save_equals_eager_savez(tmp_path):
+    """states_space streamed slab by slab into the archive == what np.savez writes."""
+    import zipfile
+
+    for env, bins in (("double_cartpole", 4), ("cartpole", 7), ("pendulum", 33)):
+        spec = envs.REGISTRY[env]
+        a, b = _shell(spec, bins=bins), _shell(spec, bins=bins)
+        rng = np.random.default_rng(1)
+        for inst in (a, b):
+            inst.value_function = rng.random(inst.n_states, dtype=np.float32)
+            inst.policy = rng.integers(0, inst.n_actions, inst.n_states).astype(np.int32)
+            rng = np.random.default_rng(1)
+        _ = a.states_space                      # a: materialised -> np.savez path;  b: streamed
+        assert b._states_space is None
+        a.save(tmp_path / f"{env}_eager")
+        b.save(tmp_path / f"{env}_streamed")
+        assert b._states_space is None          # still never materialised
+        za, zb = zipfile.ZipFile(tmp_path / f"{env}_eager.npz"), zipfile.ZipFile(tmp_path / f"{env}_streamed.npz")
+        assert za.namelist() == zb.namelist()
+        for name in za.namelist():              # same .npy bytes entry by entry (header + data)
+            assert za.read(name) == zb.read(name), name
+            assert zb.getinfo(name).compress_type == zipfile.ZIP_STORED
+        loaded = spec.cls.load(tmp_path / f"{env}_streamed")
+        assert loaded._states_space is None     # lazy: read on first use
+        np.testing.assert_array_equal(loaded.states_space, a.states_space)
+        assert loaded.n_states == a.n_states
