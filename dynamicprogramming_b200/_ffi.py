@@ -76,6 +76,7 @@ SIGNATURES = {
     "pi_abi_version": (C.c_int, []),
     "pi_device_count": (C.c_int, []),
     "pi_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "pi_nvrtc_counters": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pi_compile_check": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_int64)]),
     "pi_create": (C.c_int, [C.POINTER(PiGrid), C.POINTER(C.c_float), C.c_int32, C.POINTER(PiConfig), C.c_char_p,
                             C.c_int32, C.POINTER(PiShard), C.POINTER(C.c_void_p)]),

@@ -97,6 +97,12 @@ int pi_abi_version(void);
 /* Number of visible CUDA devices (0 when there is no driver). */
 int pi_device_count(void);
 
+/* Run-time compiles (the plugin's table builder, the grid-specialised sweeps) are cached on disk as
+ * cubins keyed by NVRTC version + options + source text: $DPB200_CACHE_DIR, else
+ * $XDG_CACHE_HOME/dpb200, else ~/.cache/dpb200; DPB200_CACHE=off disables.  Counters of this
+ * process: NVRTC compilations actually run / compilations answered from the cache. */
+int pi_nvrtc_counters(int64_t* compiles, int64_t* cache_hits);
+
 /* Compile-only check of a plugin's dynamics source against the table-builder
  * template (NVRTC, sm_100a); needs no GPU.  Errors carry the NVRTC log — the
  * analogue of cupy's CompileException at src/cuda_policy_iteration.py:289. */

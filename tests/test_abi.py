@@ -123,3 +123,45 @@ def test_product_never_imports_the_oracle():
     pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[/.](cpu_oracle|ref_runner|pi_oracle|_ref|_build)", re.M)
     for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")):
         assert not pat.search(path.read_text()), f"{path} references oracle/"
+
+
+def test_nvrtc_disk_cache(tmp_path, monkeypatch):
+    """run-time compiles are answered from a cubin cache keyed by the exact text."""
+    import ctypes as C
+
+    from dynamicprogramming_b200 import _ffi, envs
+
+    lib = _ffi.lib()
+    monkeypatch.setenv("DPB200_CACHE_DIR", str(tmp_path / "cache"))
+    monkeypatch.delenv("DPB200_CACHE", raising=False)
+    spec = envs.REGISTRY["pendulum"]
+    src = spec.cls.__new__(spec.cls)._dynamics_cuda_src()
+
+    def counters():
+        a, b = C.c_int64(), C.c_int64()
+        lib.pi_nvrtc_counters(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def compile_(text):
+        n = C.c_int64()
+        _ffi.check(lib.pi_compile_check(text.encode(), 2, C.byref(n)))
+        return n.value
+
+    c0, h0 = counters()
+    n1 = compile_(src)
+    assert counters() == (c0 + 1, h0)
+    files = list((tmp_path / "cache").glob("*.cubin"))
+    assert len(files) == 1 and files[0].stat().st_size == n1
+    assert compile_(src) == n1 and counters() == (c0 + 1, h0 + 1)            # hit: same bytes, no compile
+    compile_(src + "\n// reward weights changed\n")                           # any edit of the text misses
+    assert counters() == (c0 + 2, h0 + 1) and len(list((tmp_path / "cache").glob("*.cubin"))) == 2
+    files[0].write_bytes(b"")                                                 # a truncated entry is ignored and replaced
+    assert compile_(src) == n1 and counters() == (c0 + 3, h0 + 1) and files[0].stat().st_size == n1
+    monkeypatch.setenv("DPB200_CACHE", "off")
+    compile_(src)
+    assert counters() == (c0 + 4, h0 + 1)
+    with pytest.raises(_ffi.EngineError):                                     # errors are never cached
+        compile_("this is not CUDA")
+    monkeypatch.delenv("DPB200_CACHE")
+    with pytest.raises(_ffi.EngineError):
+        compile_("this is not CUDA")
