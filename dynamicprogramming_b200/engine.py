@@ -183,14 +183,25 @@ class _CudaPolicyIterationBase(abc.ABC):
             return np.asarray(mask, dtype=bool), float(value)
         # slab-wise over dim 0
         inner = self.n_states // len(self._axes[0])
-        rest = np.meshgrid(*self._axes[1:], indexing="ij")
-        rest_cols = [g.ravel() for g in rest]
+        chunk = np.empty((inner, self.N_DIMS), dtype=np.float32)   # one slab buffer: only column 0 changes
+        for d, g in enumerate(np.meshgrid(*self._axes[1:], indexing="ij")):
+            chunk[:, d + 1] = g.ravel()
         mask = np.empty(self.n_states, dtype=bool)
         value = 0.0
+        # per-state arrays a plugin stashes on itself inside _terminal_fn (the crane's `_goal_mask`,
+        # runners/overhead_crane_cuda.py:189) are stitched back together over the slabs
+        stashed: dict[str, list] = {}
         for i, x0 in enumerate(self._axes[0]):
-            chunk = np.column_stack([np.full(inner, x0, dtype=np.float32)] + rest_cols).astype(np.float32)
+            chunk[:, 0] = x0
+            before = {k: id(v) for k, v in vars(self).items()}
             m, value = self._terminal_fn(chunk)
             mask[i * inner:(i + 1) * inner] = m
+            for k, v in vars(self).items():
+                if isinstance(v, np.ndarray) and v.shape[:1] == (inner,) and before.get(k) != id(v):
+                    stashed.setdefault(k, []).append(v.copy())
+        for k, parts in stashed.items():
+            if len(parts) == len(self._axes[0]):
+                setattr(self, k, np.concatenate(parts))
         return mask, float(value)
 
     def _allocate_tensors_and_compile(self) -> None:

@@ -146,3 +146,23 @@ def test_streamed_save_equals_eager_savez(tmp_path):
         assert loaded._states_space is None     # lazy: read on first use
         np.testing.assert_array_equal(loaded.states_space, a.states_space)
         assert loaded.n_states == a.n_states
+
+
+def test_slabwise_terminal_mask_equals_the_full_array_path(monkeypatch):
+    from dynamicprogramming_b200 import engine
+
+    for env, bins in (("cartpole", 9), ("double_cartpole_swingup", 5), ("overhead_crane", 8), ("mountain_car", 50)):
+        inst = _shell(envs.REGISTRY[env], bins=bins)
+        full, v_full = inst._terminal_mask_and_value()
+        monkeypatch.setattr(engine, "_CHUNK_STATES", 10)      # force the slab-by-slab path
+        slab, v_slab = _shell(envs.REGISTRY[env], bins=bins)._terminal_mask_and_value()
+        monkeypatch.undo()
+        np.testing.assert_array_equal(full, slab)
+        assert v_full == v_slab and full.dtype == bool
+        if env == "overhead_crane":     # the goal mask the plugin stashes on itself covers the whole grid again
+            other = _shell(envs.REGISTRY[env], bins=bins)
+            monkeypatch.setattr(engine, "_CHUNK_STATES", 10)
+            other._terminal_mask_and_value()
+            monkeypatch.undo()
+            np.testing.assert_array_equal(other._goal_mask, inst._goal_mask)
+            assert other._goal_mask.shape == (inst.n_states,)
