@@ -112,7 +112,7 @@ SIGNATURES = {
     "pi_lookup_destroy": (None, [C.c_void_p]),
     "pi_eval_kernel_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pi_xline_compile_check": (C.c_int, [C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_int64)]),
-    "pi_debug_pair": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+    "pi_debug_pair": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "pi_debug_xline": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

@@ -7,6 +7,9 @@
 //
 //   GP_D        grid dimensions (>= 3)
 //   GP_THREADS  threads per CTA (multiple of 32)      GP_MINB   CTAs per SM
+//   GP_LV       trailing dimensions whose factors are applied per corner instead of being stored in the
+//               weight tree (1..3): the tree holds 2^(D-LV) packed nodes, every corner pays LV multiplies.
+//               Fewer tree registers leave more registers for gathers in flight (the sweep is latency-bound).
 //   gp_off[]    V offset of corner c: sum of the storage strides of the set bits (bit d <-> dim d)
 //
 // Why.  The scalar sweep (pi::eval_sweep_kernel) spends 2^D scalar FMUL for the
@@ -66,6 +69,13 @@ struct GpParams {
 #define GP_N2 ((GP_W % 4) / 2)
 #define GP_C (1 << GP_D)
 #define GP_H (GP_C / 2)
+#ifndef GP_LV
+#define GP_LV 1
+#endif
+#define GP_NT (GP_C >> GP_LV)
+#ifndef GP_G
+#define GP_G 0        // gathers per explicitly scheduled group (0: leave the schedule to ptxas)
+#endif
 
 __device__ __forceinline__ gp_u64 gp_pk(float a, float b) {
     gp_u64 r;
@@ -78,6 +88,23 @@ __device__ __forceinline__ void gp_unpk(gp_u64 v, float& a, float& b) {
 __device__ __forceinline__ gp_u64 gp_mul2(gp_u64 a, gp_u64 b) {
     gp_u64 r;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// same multiply, opaque to common-subexpression elimination (GP_LV >= 2: the partial products of the
+// trailing dimensions are RE-computed per corner, not kept in registers)
+__device__ __forceinline__ gp_u64 gp_mul2_nocse(gp_u64 a, gp_u64 b) {
+    gp_u64 r;
+    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float gp_mul_nocse(float a, float b) {
+    float r;
+    asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float gp_ld_ordered(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ gp_u64 gp_fma2(gp_u64 a, gp_u64 b, gp_u64 c) {
@@ -120,6 +147,107 @@ __device__ __forceinline__ void gp_load_row(const unsigned char* __restrict__ ta
 #endif
 }
 
+#ifndef GP_SINGLE
+#define GP_SINGLE 0   // 1: one state per thread (scalar math), same immediates and explicit gather schedule
+#endif
+
+#if GP_SINGLE
+// One state per thread: the scalar sweep (pi::eval_sweep_kernel + expected_value_grouped) with the grid's
+// strides as immediates — no address arithmetic, fewer registers, more resident warps.
+extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const GpParams p)
+{
+    const GpCtl* __restrict__ ctl = p.ctl;
+    if (ctl->done) return;
+    const int par = (ctl->base + p.j + ctl->parity0) & 1;
+    const float* __restrict__ Vin = par ? p.V1 : p.V0;
+    float* __restrict__ Vout = par ? p.V0 : p.V1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long s = (long long)blockIdx.x * GP_THREADS + threadIdx.x;
+    float res = 0.0f;
+    if (s < p.n_local) {
+        unsigned w[GP_W];
+        gp_load_row(p.rows, p.n_pad, s, w);
+        const int b = (int)w[0];
+        const float vold = Vin[p.s_begin + s];
+        float vnew;
+        if (b == -2) {
+            vnew = vold;
+        } else {
+            float ev = 0.0f;
+            if (b >= 0) {
+                const float* v = Vin + b;
+                float pre[GP_NT];
+                pre[0] = 1.0f - __uint_as_float(w[1]);
+                pre[1] = __uint_as_float(w[1]);
+#pragma unroll
+                for (int d = 1; d < GP_D - GP_LV; ++d) {
+                    const float f = __uint_as_float(w[1 + d]), g = 1.0f - f;
+#pragma unroll
+                    for (int c = GP_NT / 2 - 1; c >= 0; --c) {
+                        if (c < (1 << d)) {
+                            const float t = pre[c];
+                            pre[c + (1 << d)] = t * f;
+                            pre[c] = t * g;
+                        }
+                    }
+                }
+                float wt[GP_LV][2];
+#pragma unroll
+                for (int k = 0; k < GP_LV; ++k) {
+                    const float l = __uint_as_float(w[1 + GP_D - GP_LV + k]);
+                    wt[k][0] = 1.0f - l;
+                    wt[k][1] = l;
+                }
+#if GP_G == 0
+#pragma unroll
+                for (int c = 0; c < GP_C; ++c) {
+                    float leaf = pre[c & (GP_NT - 1)];
+#pragma unroll
+                    for (int k = 0; k < GP_LV; ++k) leaf = leaf * wt[k][(c >> (GP_D - GP_LV + k)) & 1];
+                    ev = fmaf(leaf, __ldg(v + gp_off[c]), ev);
+                }
+#else
+                float buf[2][GP_G];
+#pragma unroll
+                for (int i = 0; i < GP_G; ++i) buf[0][i] = gp_ld_ordered(v + gp_off[i]);
+#pragma unroll
+                for (int g = 0; g < GP_C / GP_G; ++g) {
+                    if (g + 1 < GP_C / GP_G) {
+#pragma unroll
+                        for (int i = 0; i < GP_G; ++i) buf[(g + 1) & 1][i] = gp_ld_ordered(v + gp_off[(g + 1) * GP_G + i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < GP_G; ++i) {
+                        const int c = g * GP_G + i;
+                        float leaf = pre[c & (GP_NT - 1)];
+#pragma unroll
+                        for (int k = 0; k < GP_LV; ++k) {
+                            const float f = wt[k][(c >> (GP_D - GP_LV + k)) & 1];
+                            leaf = (k + 1 < GP_LV) ? gp_mul_nocse(leaf, f) : leaf * f;
+                        }
+                        ev = fmaf(leaf, buf[g & 1][i], ev);
+                    }
+                }
+#endif
+            }
+            vnew = fmaf(p.gamma, ev, __uint_as_float(w[GP_D + 1]));
+        }
+        Vout[p.s_begin + s] = vnew;
+        if (p.peers.n) gp_store_peers(p.peers, par != 0, p.s_begin + s, vnew);
+        res = fabsf(vnew - vold);
+    }
+    if (!p.check) return;
+    __shared__ float s_red[32];
+    res = gp_warp_max(res);
+    if (lane == 0) s_red[warp] = res;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float r = threadIdx.x < GP_THREADS / 32 ? s_red[threadIdx.x] : 0.0f;
+        r = gp_warp_max(r);
+        if (threadIdx.x == 0) p.partial[blockIdx.x] = r;
+    }
+}
+#else
 extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const GpParams p)
 {
     const GpCtl* __restrict__ ctl = p.ctl;
@@ -149,18 +277,18 @@ extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const
         const float* vA = Vin + (bA >= 0 ? bA : 0);
         const float* vB = Vin + (bB >= 0 ? bB : 0);
 
-        // weight tree over dims 0..D-2, packed (state A, state B)
-        gp_u64 node[GP_H];
+        // weight tree over dims 0..D-1-LV, packed (state A, state B)
+        gp_u64 node[GP_NT];
         {
             const float fa = __uint_as_float(wA[1]), fb = __uint_as_float(wB[1]);
             node[0] = gp_pk(1.0f - fa, 1.0f - fb);
             node[1] = gp_pk(fa, fb);
 #pragma unroll
-            for (int d = 1; d < GP_D - 1; ++d) {
+            for (int d = 1; d < GP_D - GP_LV; ++d) {
                 const float xa = __uint_as_float(wA[1 + d]), xb = __uint_as_float(wB[1 + d]);
                 const gp_u64 f = gp_pk(xa, xb), g = gp_pk(1.0f - xa, 1.0f - xb);
 #pragma unroll
-                for (int c = GP_H / 2 - 1; c >= 0; --c) {   // constant trip count: node[] stays in registers
+                for (int c = GP_NT / 2 - 1; c >= 0; --c) {   // constant trip count: node[] stays in registers
                     if (c < (1 << d)) {
                         const gp_u64 t = node[c];
                         node[c + (1 << d)] = gp_mul2(t, f);
@@ -169,15 +297,55 @@ extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const
                 }
             }
         }
-        const float la = __uint_as_float(wA[GP_D]), lb = __uint_as_float(wB[GP_D]);
-        const gp_u64 wl0 = gp_pk(1.0f - la, 1.0f - lb), wl1 = gp_pk(la, lb);
+        // factors of the trailing dimensions D-LV .. D-1: wt[k][bit]
+        gp_u64 wt[GP_LV][2];
+#pragma unroll
+        for (int k = 0; k < GP_LV; ++k) {
+            const float la = __uint_as_float(wA[1 + GP_D - GP_LV + k]), lb = __uint_as_float(wB[1 + GP_D - GP_LV + k]);
+            wt[k][0] = gp_pk(1.0f - la, 1.0f - lb);
+            wt[k][1] = gp_pk(la, lb);
+        }
 
         gp_u64 ev = gp_pk(0.0f, 0.0f);
+#if GP_G == 0
 #pragma unroll
         for (int c = 0; c < GP_C; ++c) {
-            const gp_u64 leaf = gp_mul2(node[c & (GP_H - 1)], (c & GP_H) ? wl1 : wl0);
+            gp_u64 leaf = node[c & (GP_NT - 1)];
+#pragma unroll
+            for (int k = 0; k < GP_LV; ++k) {
+                const gp_u64 f = wt[k][(c >> (GP_D - GP_LV + k)) & 1];
+                leaf = (k + 1 < GP_LV) ? gp_mul2_nocse(leaf, f) : gp_mul2(leaf, f);
+            }
             ev = gp_fma2(leaf, gp_pk(__ldg(vA + gp_off[c]), __ldg(vB + gp_off[c])), ev);
         }
+#else
+        // explicitly scheduled gathers (see pi::expected_value_grouped): groups of GP_G corners, the loads of
+        // group g+1 are issued (volatile: in order) before the fma chain of group g consumes its values
+        float bufA[2][GP_G], bufB[2][GP_G];
+#pragma unroll
+        for (int i = 0; i < GP_G; ++i) { bufA[0][i] = gp_ld_ordered(vA + gp_off[i]); bufB[0][i] = gp_ld_ordered(vB + gp_off[i]); }
+#pragma unroll
+        for (int g = 0; g < GP_C / GP_G; ++g) {
+            if (g + 1 < GP_C / GP_G) {
+#pragma unroll
+                for (int i = 0; i < GP_G; ++i) {
+                    bufA[(g + 1) & 1][i] = gp_ld_ordered(vA + gp_off[(g + 1) * GP_G + i]);
+                    bufB[(g + 1) & 1][i] = gp_ld_ordered(vB + gp_off[(g + 1) * GP_G + i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < GP_G; ++i) {
+                const int c = g * GP_G + i;
+                gp_u64 leaf = node[c & (GP_NT - 1)];
+#pragma unroll
+                for (int k = 0; k < GP_LV; ++k) {
+                    const gp_u64 f = wt[k][(c >> (GP_D - GP_LV + k)) & 1];
+                    leaf = (k + 1 < GP_LV) ? gp_mul2_nocse(leaf, f) : gp_mul2(leaf, f);
+                }
+                ev = gp_fma2(leaf, gp_pk(bufA[g & 1][i], bufB[g & 1][i]), ev);
+            }
+        }
+#endif
         float evA, evB;
         gp_unpk(ev, evA, evB);
         // sentinel rows: terminated (-1) -> sum := 0 (:231-232); absorbing (-2) -> new_V := V (:221)
@@ -203,3 +371,4 @@ extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const
         if (threadIdx.x == 0) p.partial[blockIdx.x] = r;
     }
 }
+#endif   // GP_SINGLE

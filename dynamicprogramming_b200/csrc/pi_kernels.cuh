@@ -183,6 +183,62 @@ __device__ __forceinline__ void st_stream4(void* p, unsigned v) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// L2 eviction policies (createpolicy): the row stream is read once per sweep and should leave the L2
+// first; the gathered V window is re-read by neighbouring blocks and should stay.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ld_stream16_hint(const void* p, unsigned long long pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream8_hint(const void* p, unsigned long long pol) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+                 : "=r"(r.x), "=r"(r.y)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ unsigned ld_stream4_hint(const void* p, unsigned long long pol) {
+    unsigned r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ld_keep4(const float* p, unsigned long long pol) {
+    float r;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
+// load_row with an L2 eviction policy on every plane
+template <int D>
+__device__ __forceinline__ void load_row_hint(const unsigned char* __restrict__ tab, long long n_pad, long long s,
+                                              unsigned (&w)[Row<D>::W], unsigned long long pol) {
+    using R = Row<D>;
+#pragma unroll
+    for (int p = 0; p < R::N4; ++p) {
+        uint4 v = ld_stream16_hint(tab + (size_t)p * 16u * (size_t)n_pad + (size_t)s * 16u, pol);
+        w[4 * p + 0] = v.x; w[4 * p + 1] = v.y; w[4 * p + 2] = v.z; w[4 * p + 3] = v.w;
+    }
+    if constexpr (R::N2 != 0) {
+        uint2 v = ld_stream8_hint(tab + (size_t)R::N4 * 16u * (size_t)n_pad + (size_t)s * 8u, pol);
+        w[4 * R::N4 + 0] = v.x; w[4 * R::N4 + 1] = v.y;
+    }
+    if constexpr (R::N1 != 0) {
+        w[R::W - 1] = ld_stream4_hint(tab + ((size_t)R::N4 * 16u + (size_t)R::N2 * 8u) * (size_t)n_pad + (size_t)s * 4u, pol);
+    }
+}
+
 // Load the row of local state `s` from the table that starts at `tab`.
 template <int D>
 __device__ __forceinline__ void load_row(const unsigned char* __restrict__ tab, long long n_pad, long long s,
@@ -236,10 +292,105 @@ __host__ __device__ constexpr int corner_bit(int c, int d) {
 // accumulated as ev = fmaf(w_c, V[idx_c], ev) for c = 0 .. 2^D-1 from ev = 0
 // (:236-239, :643-646, :1074-1076).  Prefix products are shared between corners
 // (same multiplication order per corner, so the same rounding).
-template <int D>
+__device__ __forceinline__ float ld_nc_ordered(const float* p) {   // volatile: keeps its place among the other gathers
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// Explicitly scheduled form of expected_value (same arithmetic, same order): the 2^D gathers are issued in
+// groups of G back-to-back loads, group g+1 before the fma chain of group g consumes its values, so a
+// warp always has G..2G gathers in flight whatever ptxas would have hoisted (the sweep is latency-bound:
+// measured 1.54 / 1.68 / 1.91 ms for 25 / 21 / 19 leading loads in otherwise equal code).  Weight tree
+// over the first D-2 dims, the last two factors applied per corner.
+template <int D, int G>
+__device__ __forceinline__ float expected_value_grouped(const float* __restrict__ V, int base,
+                                                        const float (&frac)[D], const int (&stride)[D]) {
+    static_assert(D >= 4, "grouped form needs D >= 4");
+    constexpr int C = 1 << D, Q = C / 4, NG = C / G;
+    static_assert(C % G == 0 && NG >= 1, "G must divide 2^D");
+    float pre[Q];
+    pre[0] = 1.0f - frac[0];
+    pre[1] = frac[0];
+#pragma unroll
+    for (int d = 1; d < D - 2; ++d) {
+        const float g = 1.0f - frac[d];
+#pragma unroll
+        for (int c = (1 << d) - 1; c >= 0; --c) {
+            const float p = pre[c];
+            pre[c + (1 << d)] = p * frac[d];
+            pre[c] = p * g;
+        }
+    }
+    const float fm = frac[D - 2], gm = 1.0f - fm, fl = frac[D - 1], gl = 1.0f - fl;
+    const float* v = V + base;
+    float buf[2][G];
+    auto off_of = [&](int c) {
+        int off = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            if (corner_bit<D>(c, d)) off += stride[d];
+        return off;
+    };
+#pragma unroll
+    for (int i = 0; i < G; ++i) buf[0][i] = ld_nc_ordered(v + off_of(i));
+    float ev = 0.0f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (g + 1 < NG) {
+#pragma unroll
+            for (int i = 0; i < G; ++i) buf[(g + 1) & 1][i] = ld_nc_ordered(v + off_of((g + 1) * G + i));
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int c = g * G + i;
+            const float w = (pre[c & (Q - 1)] * (((c >> (D - 2)) & 1) ? fm : gm)) * ((c >> (D - 1)) ? fl : gl);
+            ev = fmaf(w, buf[g & 1][i], ev);
+        }
+    }
+    return ev;
+}
+
+template <int D, bool KEEP = false, int LV = 0>
 __device__ __forceinline__ float expected_value(const float* __restrict__ V, int base,
-                                                const float (&frac)[D], const int (&stride)[D]) {
+                                                const float (&frac)[D], const int (&stride)[D],
+                                                unsigned long long keep_pol = 0ull) {
     constexpr int C = 1 << D;
+    if constexpr (LV == 1 && D >= 4) {
+        // Register-lean form: prefix products over the first D-2 dims only (2^(D-2) registers instead of
+        // 2^(D-1)); the factors of dims D-2 and D-1 are applied per corner, in the same left-to-right
+        // order ((pre * f_{D-2}) * f_{D-1}) — one more multiply per corner, identical rounding.
+        constexpr int Q = C / 4;
+        float pre[Q];
+        pre[0] = 1.0f - frac[0];
+        pre[1] = frac[0];
+#pragma unroll
+        for (int d = 1; d < D - 2; ++d) {
+            const float g = 1.0f - frac[d];
+#pragma unroll
+            for (int c = (1 << d) - 1; c >= 0; --c) {
+                const float p = pre[c];
+                pre[c + (1 << d)] = p * frac[d];
+                pre[c] = p * g;
+            }
+        }
+        const float fm = frac[D - 2], gm = 1.0f - fm, fl = frac[D - 1], gl = 1.0f - fl;
+        const float* v = V + base;
+        float ev = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            int off = 0;
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                if (corner_bit<D>(c, d)) off += stride[d];
+            float x;
+            if constexpr (KEEP) x = ld_keep4(v + off, keep_pol);
+            else x = v[off];
+            const float w = (pre[c & (Q - 1)] * (((c >> (D - 2)) & 1) ? fm : gm)) * ((c >> (D - 1)) ? fl : gl);
+            ev = fmaf(w, x, ev);
+        }
+        return ev;
+    } else
     if constexpr (D == 1) {
         const float* v = V + base;
         float ev = fmaf(1.0f - frac[0], v[0], 0.0f);
@@ -279,7 +430,8 @@ __device__ __forceinline__ float expected_value(const float* __restrict__ V, int
 #pragma unroll
             for (int d = 0; d < D; ++d)
                 if (corner_bit<D>(c, d)) off += stride[d];
-            val[c] = v[off];
+            if constexpr (KEEP) val[c] = ld_keep4(v + off, keep_pol);
+            else val[c] = v[off];
         }
         float ev = 0.0f;
 #pragma unroll
@@ -363,6 +515,9 @@ struct EvalParams {
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2_bulk_hint(const void* p, unsigned bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
+}
 
 // Blocks are scheduled in index order, so at any moment all SMs work in one
 // neighbourhood of the state space and share its V window in L2 (a persistent kernel
@@ -371,8 +526,22 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
 // row stream at the start of every block; one thread per block therefore issues a TMA
 // bulk prefetch into L2 of the row planes (and the old values) that the block
 // `p.lookahead` positions later will read.
-template <int D>
-__global__ void __launch_bounds__(kBlock) eval_sweep_kernel(const EvalParams p) {
+// VAR (tuning variants, selected by DPB200_EVAL_VARIANT; all bit-identical):
+//   bit 0: L2 evict-first policy on the row stream (loads and the TMA prefetch)
+//   bit 1: L2 evict-last policy on the V gathers
+//   bits 2-4: minimum resident blocks per SM forced through __launch_bounds__:
+//             0 -> unspecified (compiler heuristic), 1 -> 1, 2 -> 3, 3 -> 4, 4 -> 5, 5 -> 6, 6 -> 8
+__host__ __device__ constexpr int eval_variant_minb(int var) {
+    constexpr int t[8] = {0, 1, 3, 4, 5, 6, 8, 0};
+    return t[(var >> 2) & 7];
+}
+template <int D, int VAR = 0>
+__global__ void __launch_bounds__(kBlock, eval_variant_minb(VAR)) eval_sweep_kernel(const EvalParams p) {
+    constexpr bool ROW_EF = (VAR & 1) != 0, V_KEEP = (VAR & 2) != 0;
+    constexpr int LEAN = (VAR >> 5) & 1;   // bit 5: register-lean weight tree (expected_value LV = 1)
+    // bits 6-8: explicitly scheduled gathers in groups of 8 / 16 / 32 / 4 / 2 (expected_value_grouped)
+    constexpr int kGroupOf[8] = {0, 8, 16, 32, 4, 2, 0, 0};
+    constexpr int GROUP = kGroupOf[(VAR >> 6) & 7];
     const Ctl* __restrict__ ctl = p.ctl;
     if (ctl->done) return;
     const int par = (ctl->base + p.j + ctl->parity0) & 1;
@@ -385,11 +554,20 @@ __global__ void __launch_bounds__(kBlock) eval_sweep_kernel(const EvalParams p) 
             using R = Row<D>;
             const long long left = p.n_pad - s_pf;
             const unsigned n = (unsigned)(left < kBlock ? left : kBlock);
+            if constexpr (ROW_EF) {
+                const unsigned long long pol = l2_policy_evict_first();
 #pragma unroll
-            for (int q = 0; q < R::N4; ++q)
-                prefetch_l2_bulk(p.rows + (size_t)q * 16u * (size_t)p.n_pad + (size_t)s_pf * 16u, n * 16u);
-            if constexpr (R::N2 != 0)
-                prefetch_l2_bulk(p.rows + (size_t)R::N4 * 16u * (size_t)p.n_pad + (size_t)s_pf * 8u, n * 8u);
+                for (int q = 0; q < R::N4; ++q)
+                    prefetch_l2_bulk_hint(p.rows + (size_t)q * 16u * (size_t)p.n_pad + (size_t)s_pf * 16u, n * 16u, pol);
+                if constexpr (R::N2 != 0)
+                    prefetch_l2_bulk_hint(p.rows + (size_t)R::N4 * 16u * (size_t)p.n_pad + (size_t)s_pf * 8u, n * 8u, pol);
+            } else {
+#pragma unroll
+                for (int q = 0; q < R::N4; ++q)
+                    prefetch_l2_bulk(p.rows + (size_t)q * 16u * (size_t)p.n_pad + (size_t)s_pf * 16u, n * 16u);
+                if constexpr (R::N2 != 0)
+                    prefetch_l2_bulk(p.rows + (size_t)R::N4 * 16u * (size_t)p.n_pad + (size_t)s_pf * 8u, n * 8u);
+            }
         }
     }
 
@@ -397,7 +575,8 @@ __global__ void __launch_bounds__(kBlock) eval_sweep_kernel(const EvalParams p) 
     float res = 0.0f;
     if (s < p.n_local) {
         unsigned w[Row<D>::W];
-        load_row<D>(p.rows, p.n_pad, s, w);
+        if constexpr (ROW_EF) load_row_hint<D>(p.rows, p.n_pad, s, w, l2_policy_evict_first());
+        else load_row<D>(p.rows, p.n_pad, s, w);
         const int base = (int)w[0];
         const float vold = Vin[p.s_begin + s];
         float vnew;
@@ -410,7 +589,9 @@ __global__ void __launch_bounds__(kBlock) eval_sweep_kernel(const EvalParams p) 
                 int stride[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) { frac[d] = __uint_as_float(w[1 + d]); stride[d] = p.stride[d]; }
-                ev = expected_value<D>(Vin, base, frac, stride);
+                if constexpr (GROUP != 0 && D >= 4) ev = expected_value_grouped<D, (GROUP < (1 << D) ? GROUP : (1 << D))>(Vin, base, frac, stride);
+                else if constexpr (V_KEEP) ev = expected_value<D, true, LEAN>(Vin, base, frac, stride, l2_policy_evict_last());
+                else ev = expected_value<D, false, LEAN>(Vin, base, frac, stride);
             }
             vnew = fmaf(p.gamma, ev, __uint_as_float(w[D + 1]));  // reward + gamma*ev contracts to one FMA
         }

@@ -227,11 +227,13 @@ int pi_xline_compile_check(int32_t n_dims, int32_t bins, const char* cfg, int64_
 int pi_debug_xline(pi_engine* e, const char* cfg, int32_t iters, float* ms_xline, float* ms_scalar,
                    int64_t* mismatches, double* window_fraction, int32_t* info);
 
-/* Test hook: the packed-pair generic sweep (csrc/pair_sweep_src.cuh: two states per thread,
- * FMUL2/FFMA2, gather addresses as immediates; JIT) vs the scalar sweep; engine state unchanged.
- * DPB200_PAIR = off (default) | auto | force | <threads>,<minb> controls the build-time selection. */
-int pi_debug_pair(pi_engine* e, int32_t threads, int32_t minb, int32_t iters, float* ms_pair, float* ms_scalar,
-                  int64_t* mismatches, int32_t* regs);
+/* Test hook for the JIT sweeps of csrc/pair_sweep_src.cuh (grid strides as immediates): compiles the
+ * configuration (threads per block, blocks per SM, lean weight-tree levels 1..3, gathers per explicitly
+ * scheduled group or 0, single = 1: one state per thread / 0: two states per thread with packed f32x2
+ * math), runs it and the scalar sweep `iters` times on the current rows and V, and counts differing words
+ * of the result (must be 0). */
+int pi_debug_pair(pi_engine* e, int32_t threads, int32_t minb, int32_t lv, int32_t group, int32_t single, int32_t iters,
+                  float* ms_pair, float* ms_scalar, int64_t* mismatches, int32_t* regs);
 
 /* N2: batched policy lookup with get_optimal_action semantics — action(p) = sum_c lambda_c(p) *
  * action_space[policy[idx_c(p)]] (utils/barycentric.py:76-108; weights and indices as

@@ -27,12 +27,16 @@ td = pdist.init_process_group()
 # scalar sweep, so the x-line cases also prove: sharded x-line sweep == unsharded scalar sweep, bit for bit
 XL = {"DPB200_FAST_DIM": "0", "DPB200_XLINE": "force:2,0,4,8,2,1:1,1,1,8,8"}
 XL4 = {"DPB200_FAST_DIM": "0", "DPB200_XLINE": "force:4,0,4,8,1,1:1,6,12"}
+# the JIT generic sweeps (one state per thread with grouped gathers — the default of large 6-D grids — and packed pairs)
+GP1 = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:128,8,2,8,1"}
+GP2 = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:64,8,2,8,0"}
 cases = [("cartpole", 12, 4, {}), ("mountain_car", 60, None, {}), ("double_pendulum_swingup", 10, 3, {}),
          ("double_cartpole_swingup", 7, 2, {}), ("pendulum", 33, 6, {}),
-         ("double_cartpole_swingup", 8, 2, XL), ("cartpole_swingup", 12, 3, XL4)]
+         ("double_cartpole_swingup", 8, 2, XL), ("cartpole_swingup", 12, 3, XL4),
+         ("double_cartpole_swingup", 7, 2, GP1), ("cartpole_swingup", 11, 3, GP1), ("double_cartpole", 6, 2, GP2)]
 ok = True
 for env, bins, max_pi, engine_env in cases:
-    for k in ("DPB200_FAST_DIM", "DPB200_XLINE"):
+    for k in ("DPB200_FAST_DIM", "DPB200_XLINE", "DPB200_PAIR"):
         os.environ.pop(k, None)
     os.environ.update(engine_env)
     spec = envs.REGISTRY[env]
@@ -43,12 +47,15 @@ for env, bins, max_pi, engine_env in cases:
     eng = spec.make(bins=bins, config=cfg, device=local, shard=shard)
     eng.build_table()
     kernel = eng.eval_kernel_info()["kernel"]
-    if engine_env:
+    if "DPB200_PAIR" in engine_env:
+        assert "gp_sweep" in kernel, kernel
+    elif engine_env:
         assert "xl_sweep" in kernel, kernel
     eng.run()
     res = dict(env=env, bins=bins, N=eng.n_states, pi=eng.pi_iterations, sweeps=eng.total_eval_sweeps, kernel=kernel[:40])
     if rank == 0:
         os.environ["DPB200_XLINE"] = "off"
+        os.environ["DPB200_PAIR"] = "off"
         one = spec.make(bins=bins, config=cfg, device=local)
         one.run()
         res.update(pi_1gpu=one.pi_iterations, sweeps_1gpu=one.total_eval_sweeps,

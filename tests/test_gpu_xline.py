@@ -123,7 +123,53 @@ def test_packed_pair_sweep_is_bit_identical_to_the_scalar_sweep(env, bins, monke
     for threads, minb in ((64, 8), (256, 2)):
         out = eng.debug_pair(threads, minb, iters=1)
         assert out["mismatches"] == 0, out
+    # lean weight-tree levels and explicitly scheduled gather groups, packed pairs and ONE state per thread
+    # (the default generic sweep of large 6-D grids: 128 x 8, lv 2, groups of 8)
+    for threads, minb, lv, group, single in ((64, 8, 2, 8, False), (128, 4, 3, 16, False), (128, 8, 2, 8, True),
+                                             (128, 8, 1, 0, True), (256, 4, 3, 4, True), (128, 16, 1, 0, True),
+                                             (64, 16, 2, 16, True)):
+        out = eng.debug_pair(threads, minb, iters=1, lv=lv, group=group, single=single)
+        assert out["mismatches"] == 0, (threads, minb, lv, group, single, out)
     eng.close()
+
+
+@pytest.mark.parametrize("variant", [2, 12, 44, 64, 128, 192, 256])
+def test_scalar_sweep_tuning_variants_are_bit_identical(variant, monkeypatch):
+    """DPB200_EVAL_VARIANT (L2 eviction policies, forced occupancy, lean weight tree, explicitly grouped gathers):
+    same V bits as the default scalar sweep on a 6-D and a 4-D environment."""
+    monkeypatch.setenv("DPB200_XLINE", "off")
+    monkeypatch.setenv("DPB200_PAIR", "off")
+    for env, bins in (("double_cartpole_swingup", 7), ("cartpole_swingup", 15)):
+        res = []
+        for var in (0, variant):
+            monkeypatch.setenv("DPB200_EVAL_VARIANT", str(var))
+            eng = envs.make(env, bins=bins)
+            eng.build_table()
+            eng.sweeps(20)
+            eng.policy_improvement()
+            eng.sweeps(7)
+            v, _ = eng.download()
+            res.append(bits(v).copy())
+            eng.close()
+        np.testing.assert_array_equal(res[0], res[1])
+
+
+def test_full_policy_iteration_with_the_single_state_jit_sweep_matches_the_reference(monkeypatch, ref_runner):
+    monkeypatch.setenv("DPB200_XLINE", "off")
+    monkeypatch.setenv("DPB200_PAIR", "force:128,8,2,8,1")
+    for env, bins in (("double_cartpole_swingup", 6), ("cartpole", 12)):
+        spec = envs.REGISTRY[env]
+        c = spec.config()
+        c.max_pi_iter, c.max_eval_iter = 3, 200
+        eng = spec.make(bins=bins, config=c)
+        eng.build_table()
+        assert "one state/thread" in eng.eval_kernel_info()["kernel"]
+        ref = ref_runner.from_engine_env(env, bins=bins, config=c)
+        eng.run()
+        ref.run()
+        assert eng.total_eval_sweeps == ref.total_sweeps and eng.pi_iterations == ref.pi_iterations
+        np.testing.assert_array_equal(eng.policy, ref.policy)
+        np.testing.assert_array_equal(bits(eng.value_function), bits(ref.value_function))
 
 
 def test_full_policy_iteration_with_the_packed_pair_sweep_matches_the_reference(monkeypatch, ref_runner):
