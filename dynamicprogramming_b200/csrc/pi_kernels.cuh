@@ -351,7 +351,15 @@ __device__ __forceinline__ float expected_value_grouped(const float* __restrict_
     return ev;
 }
 
-template <int D, bool KEEP = false, int LV = 0>
+// CG = true: gathers bypass the L1 (ld.global.cg) — the persistent multi-sweep kernel reads values other
+// SMs wrote one grid barrier ago, and the L1 is not coherent.
+template <bool CG>
+__device__ __forceinline__ float ld_v(const float* p) {
+    if constexpr (CG) return __ldcg(p);
+    else return *p;
+}
+
+template <int D, bool KEEP = false, int LV = 0, bool CG = false>
 __device__ __forceinline__ float expected_value(const float* __restrict__ V, int base,
                                                 const float (&frac)[D], const int (&stride)[D],
                                                 unsigned long long keep_pol = 0ull) {
@@ -393,12 +401,13 @@ __device__ __forceinline__ float expected_value(const float* __restrict__ V, int
     } else
     if constexpr (D == 1) {
         const float* v = V + base;
-        float ev = fmaf(1.0f - frac[0], v[0], 0.0f);
-        return fmaf(frac[0], v[stride[0]], ev);
+        float ev = fmaf(1.0f - frac[0], ld_v<CG>(v), 0.0f);
+        return fmaf(frac[0], ld_v<CG>(v + stride[0]), ev);
     } else if constexpr (D == 2) {
         const float g0 = 1.0f - frac[0], g1 = 1.0f - frac[1];
         const float* v = V + base;
-        const float v00 = v[0], v01 = v[stride[1]], v10 = v[stride[0]], v11 = v[stride[0] + stride[1]];
+        const float v00 = ld_v<CG>(v), v01 = ld_v<CG>(v + stride[1]), v10 = ld_v<CG>(v + stride[0]),
+                    v11 = ld_v<CG>(v + stride[0] + stride[1]);
         float ev = 0.0f;
         ev = fmaf(g0 * g1, v00, ev);
         ev = fmaf(g0 * frac[1], v01, ev);
@@ -431,7 +440,7 @@ __device__ __forceinline__ float expected_value(const float* __restrict__ V, int
             for (int d = 0; d < D; ++d)
                 if (corner_bit<D>(c, d)) off += stride[d];
             if constexpr (KEEP) val[c] = ld_keep4(v + off, keep_pol);
-            else val[c] = v[off];
+            else val[c] = ld_v<CG>(v + off);
         }
         float ev = 0.0f;
 #pragma unroll
@@ -610,6 +619,155 @@ __global__ void __launch_bounds__(kBlock, eval_variant_minb(VAR)) eval_sweep_ker
         float r = threadIdx.x < kBlock / 32 ? s_red[threadIdx.x] : 0.0f;
         r = warp_max(r);
         if (threadIdx.x == 0) p.partial[blockIdx.x] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Persistent multi-sweep evaluation for grids that fit the chip: ONE cooperative launch runs a whole
+// batch of sweeps (up to a sync interval of policy_evaluation(), src/cuda_policy_iteration.py:300-336).
+// Small grids (K1 Pendulum 200^2, K2 Continuous Mountain Car 400^2) are launch-bound in the per-sweep
+// form: 2.4 us per sweep of which the Bellman backups are a fraction.  Here every thread keeps the rows
+// of its (up to SPT) states in registers for the whole batch, V lives in L2 (gathers bypass the
+// non-coherent L1), sweeps are separated by a grid barrier (one release-arrive + acquire-spin per block on a
+// monotonic counter) instead of a kernel boundary, and the residual reduction + bookkeeping of
+// eval_reduce_kernel is done by the last block to finish.  Same arithmetic, same order, same sweep counts.
+// ---------------------------------------------------------------------------
+constexpr int kPBlock = 512;
+
+struct PersistParams {
+    const unsigned char* rows;
+    float* V0;
+    float* V1;
+    Ctl* ctl;
+    float* partial;      // [gridDim.x]
+    unsigned* bar;       // [0] barrier arrivals, [1] finish tickets — zeroed before every launch
+    long long n_local;
+    long long n_pad;
+    float gamma;
+    float theta;
+    int k;               // sweeps in this launch
+    int has_check;       // reduce the residual of the last sweep
+    int decide;          // ... and apply delta < theta (kBatchDecide)
+    int stride[kMaxDims];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All blocks are co-resident (cooperative launch).  `target` counts arrivals expected so far.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();   // this block's V stores are visible before its arrival is
+        atomicAdd(bar, 1u);
+        while (ld_acquire_u32(bar) < target) { }
+    }
+    __syncthreads();
+}
+
+template <int D, int SPT>
+__global__ void __launch_bounds__(kPBlock) eval_persistent_kernel(const PersistParams p) {
+    Ctl* ctl = p.ctl;
+    if (ctl->done) return;   // written by an earlier launch: every block sees the same value
+    const int par0 = (ctl->base + ctl->parity0) & 1;
+    const long long tid = (long long)blockIdx.x * kPBlock + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * kPBlock;
+
+    unsigned w[SPT][Row<D>::W];
+    float vcur[SPT];
+    bool in[SPT];
+    int stride[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) stride[d] = p.stride[d];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+        const long long s = tid + i * nthreads;
+        in[i] = s < p.n_local;
+        vcur[i] = 0.0f;
+        if (in[i]) {
+            load_row<D>(p.rows, p.n_pad, s, w[i]);
+            vcur[i] = __ldcg((par0 ? p.V1 : p.V0) + s);
+        }
+    }
+
+    unsigned target = 0;
+    float res = 0.0f;
+    for (int j = 0; j < p.k; ++j) {
+        const int par = (par0 + j) & 1;
+        const float* Vin = par ? p.V1 : p.V0;
+        float* Vout = par ? p.V0 : p.V1;
+        const bool last = j == p.k - 1;
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) {
+            if (!in[i]) continue;
+            const int base = (int)w[i][0];
+            const float vold = vcur[i];
+            float vnew;
+            if (base == PI_ROW_ABSORBING) {
+                vnew = vold;
+            } else {
+                float ev = 0.0f;
+                if (base >= 0) {
+                    float frac[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) frac[d] = __uint_as_float(w[i][1 + d]);
+                    ev = expected_value<D, false, 0, true>(Vin, base, frac, stride);
+                }
+                vnew = fmaf(p.gamma, ev, __uint_as_float(w[i][D + 1]));
+            }
+            __stcg(Vout + tid + i * nthreads, vnew);
+            vcur[i] = vnew;
+            if (last) res = fmaxf(res, fabsf(vnew - vold));
+        }
+        if (!last) grid_barrier(p.bar, target);
+    }
+
+    // residual of the last sweep -> partial[block]; the last block to finish reduces and keeps the books
+    __shared__ float s_red[kPBlock / 32];
+    __shared__ int s_is_last;
+    if (p.has_check) {
+        res = warp_max(res);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = res;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float r = threadIdx.x < kPBlock / 32 ? s_red[threadIdx.x] : 0.0f;
+            r = warp_max(r);
+            if (threadIdx.x == 0) __stcg(p.partial + blockIdx.x, r);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_is_last = atomicAdd(p.bar + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    float r = 0.0f;
+    if (p.has_check) {
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kPBlock) r = fmaxf(r, __ldcg(p.partial + b));
+        r = warp_max(r);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = r;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            r = threadIdx.x < kPBlock / 32 ? s_red[threadIdx.x] : 0.0f;
+            r = warp_max(r);
+        }
+    }
+    if (threadIdx.x == 0) {   // == eval_reduce_kernel
+        ctl->base += p.k;
+        if (p.has_check) {
+            ctl->last_delta = r;
+            if (p.decide) {
+                ctl->check_delta = r;
+                if (r < p.theta) { ctl->done = 1; ctl->conv_sweep = ctl->base - 1; }
+            }
+        }
     }
 }
 

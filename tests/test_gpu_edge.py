@@ -224,3 +224,23 @@ def test_local_policy_upload_equals_the_full_upload():
     np.testing.assert_array_equal(res[0][0], res[1][0])
     np.testing.assert_array_equal(res[0][1], res[1][1])
     np.testing.assert_array_equal(res[0][1], P)
+
+
+@pytest.mark.parametrize("env,bins", [("pendulum", 64), ("mountain_car", 90), ("cartpole", 11), ("overhead_crane", 9)])
+def test_persistent_multi_sweep_kernel_matches_the_reference(env, bins, monkeypatch, ref_runner):
+    """DPB200_PERSIST=on: one cooperative launch per sync interval (grid barrier between sweeps, rows in
+    registers, L1-bypassing gathers) — same sweep counts, policy and V bits as the reference's kernels."""
+    monkeypatch.setenv("DPB200_PERSIST", "on")
+    monkeypatch.setenv("DPB200_XLINE", "off")
+    spec = envs.REGISTRY[env]
+    cfg = spec.config()
+    cfg.max_pi_iter = 4
+    eng = spec.make(bins=bins, config=cfg)
+    eng.build_table()
+    assert "eval_persistent_kernel" in eng.eval_kernel_info()["kernel"]
+    ref = ref_runner.from_engine_env(env, bins=bins, config=cfg)
+    eng.run()
+    ref.run()
+    assert eng.total_eval_sweeps == ref.total_sweeps and eng.pi_iterations == ref.pi_iterations
+    np.testing.assert_array_equal(eng.policy, ref.policy)
+    np.testing.assert_array_equal(bits(eng.value_function), bits(ref.value_function))
