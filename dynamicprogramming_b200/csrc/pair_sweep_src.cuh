@@ -1,8 +1,15 @@
-// pair_sweep_src.cuh — CUDA source of the packed-pair evaluation sweep: the generic gather
-// sweep (policy_eval_kernel_4d/_6d of the reference, src/cuda_policy_iteration.py:616-649,
-// :1044-1079, + the max|x-y| reduction :563-571, :987-995) with TWO states per thread whose
-// weight trees and fma chains run as one packed mul.rn.f32x2 / fma.rn.f32x2 stream, compiled
-// at run time by NVRTC for sm_100a with the grid strides baked in as immediates.
+// pair_sweep_src.cuh — CUDA source of the JIT generic evaluation sweeps: the gather sweep
+// (policy_eval_kernel_4d/_6d of the reference, src/cuda_policy_iteration.py:616-649, :1044-1079,
+// + the max|x-y| reduction :563-571, :987-995) compiled at run time by NVRTC for sm_100a with the
+// grid strides baked in as immediates.  Two forms, one entry point (gp_sweep):
+//
+//   GP_SINGLE = 1  ONE state per thread, scalar math, the 2^D gathers issued in explicit groups of
+//                  GP_G loads with the next group in flight while the fma chain consumes the current
+//                  one — the default generic sweep of large 6-D grids (K5: 1.47 vs 1.68 ms per sweep
+//                  for the ahead-of-time kernel; L1 data pipe 81 % busy)
+//   GP_SINGLE = 0  TWO states per thread whose weight trees and fma chains run as one packed
+//                  mul.rn.f32x2 / fma.rn.f32x2 stream (opt-in; the FMA pipe is not the limit)
+//
 // build.py turns this file into the string pi::kPairSweepSrc; the host prepends
 //
 //   GP_D        grid dimensions (>= 3)
@@ -10,9 +17,10 @@
 //   GP_LV       trailing dimensions whose factors are applied per corner instead of being stored in the
 //               weight tree (1..3): the tree holds 2^(D-LV) packed nodes, every corner pays LV multiplies.
 //               Fewer tree registers leave more registers for gathers in flight (the sweep is latency-bound).
+//   GP_G        gathers per explicitly scheduled group (0: leave the schedule to ptxas)
 //   gp_off[]    V offset of corner c: sum of the storage strides of the set bits (bit d <-> dim d)
 //
-// Why.  The scalar sweep (pi::eval_sweep_kernel) spends 2^D scalar FMUL for the
+// Why the packed form.  The scalar sweep (pi::eval_sweep_kernel) spends 2^D scalar FMUL for the
 // leaf weights, 2^D-4 for the tree, 2^D FFMA for the chain and ~2^D IMAD for the gather
 // addresses per state — all on the FMA pipe, where a 3-register FFMA/FMUL/IMAD issues at half
 // rate on sm_100.  Here the two states of a thread share every FMA-pipe instruction (each
