@@ -1183,6 +1183,12 @@ __global__ void expand_rows_kernel(const unsigned char* table, long long n_pad, 
     }
 }
 
+// Pair shadow of V for the JIT sweep's GP_PAIRV mode: P[i] = (V[i], V[i+1]) (the last pair's second half is never read).
+__global__ void make_pairs_kernel(const float* __restrict__ V, float2* __restrict__ P, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) P[i] = make_float2(V[i], i + 1 < n ? V[i + 1] : 0.0f);
+}
+
 // V[s] = value where mask (reference order) is set; V buffers are in internal order.
 __global__ void fill_masked_kernel(GridDesc g, float* V0, float* V1, const unsigned char* mask_ref, long long n,
                                    float value) {

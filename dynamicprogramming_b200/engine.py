@@ -496,11 +496,12 @@ class _CudaPolicyIterationBase(abc.ABC):
                 "window_fraction": wf.value, "registers": int(info[0]), "grid": int(info[1]), "block": int(info[2])}
 
     def debug_pair(self, threads: int = 256, minb: int = 2, iters: int = 5, lv: int = 1, group: int = 0,
-                   single: bool = False) -> dict:
-        """Test hook: a JIT sweep configuration (packed pairs or one state per thread, csrc/pair_sweep_src.cuh)
-        vs the scalar sweep (bitwise comparison + timings)."""
+                   single: int = 0) -> dict:
+        """Test hook: a JIT sweep configuration (csrc/pair_sweep_src.cuh; single = 0 packed pairs, 1 one state per
+        thread, 2 one state per thread gathering from the pair shadow of V) vs the scalar sweep (bitwise
+        comparison + timings)."""
         ms_p, ms_s, mism, regs = C.c_float(), C.c_float(), C.c_int64(), C.c_int32()
-        _ffi.check(_ffi.lib().pi_debug_pair(self._engine, int(threads), int(minb), int(lv), int(group), int(bool(single)),
+        _ffi.check(_ffi.lib().pi_debug_pair(self._engine, int(threads), int(minb), int(lv), int(group), int(single),
                                             int(iters), C.byref(ms_p), C.byref(ms_s), C.byref(mism), C.byref(regs)))
         return {"ms_pair": ms_p.value, "ms_scalar": ms_s.value, "mismatches": int(mism.value), "registers": int(regs.value)}
 

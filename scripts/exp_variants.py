@@ -39,7 +39,7 @@ for cfg in cfgs:
     v, _ = eng.download()
     h = hashlib.sha1(v.tobytes()).hexdigest()[:12]
     ref_hash = ref_hash or h
-    print(f"{cfg:60s} ms/sweep min {min(ms):.4f} med {sorted(ms)[len(ms)//2]:.4f}  V {h} {'OK' if h == ref_hash else 'MISMATCH'}  [{eng.eval_kernel_info()['kernel'][:40]}]", flush=True)
+    print(f"{cfg:60s} ms/sweep min {min(ms):.4f} med {sorted(ms)[len(ms)//2]:.4f}  V {h} {'OK' if h == ref_hash else 'MISMATCH'}  [{eng.eval_kernel_info()["kernel"][:58]}]", flush=True)
     eng.close()
     for k, v0 in old.items():
         if v0 is None: os.environ.pop(k, None)

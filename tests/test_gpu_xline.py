@@ -130,6 +130,12 @@ def test_packed_pair_sweep_is_bit_identical_to_the_scalar_sweep(env, bins, monke
                                              (64, 16, 2, 16, True)):
         out = eng.debug_pair(threads, minb, iters=1, lv=lv, group=group, single=single)
         assert out["mismatches"] == 0, (threads, minb, lv, group, single, out)
+    # pair-shadow gathers (P[i] = (V[i], V[i+1]), one 64-bit load per cell edge along the fast dimension): needs
+    # logical dimension 0 stored fastest
+    if eng.layout()["fast_dim"] == 0:
+        for group in (2, 8, 16):
+            out = eng.debug_pair(128, 8, iters=2, lv=2, group=group, single=2)
+            assert out["mismatches"] == 0, (group, out)
     eng.close()
 
 
