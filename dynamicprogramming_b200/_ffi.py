@@ -114,6 +114,8 @@ SIGNATURES = {
     "pi_xline_compile_check": (C.c_int, [C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_int64)]),
     "pi_debug_pair": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "pi_debug_plane": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "pi_debug_xline": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
 }

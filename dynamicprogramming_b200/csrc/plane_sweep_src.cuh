@@ -1,0 +1,445 @@
+// plane_sweep_src.cuh — CUDA source of the PLANE-STAGED evaluation sweep (JIT, NVRTC, sm_100a).
+//
+// The same Bellman backup as policy_eval_kernel_4d/_6d of the reference
+// (src/cuda_policy_iteration.py:616-649, :1044-1079) + the max|x-y| reduction (:563-571, :987-995),
+// but the 2^D values of V a backup needs are read from SHARED MEMORY, not gathered through the L1:
+//
+//   * the two fastest-stored dimensions (f0 fastest, f1 next) span a "V-plane" of PS_P = n_f0 * n_f1
+//     floats that is contiguous and 16-byte aligned in HBM; the other D-2 dimensions enumerate planes;
+//   * one CTA walks a chunk of PS_L consecutive state-planes.  All states of a plane that take the same
+//     action land in the same cell of the outer dimensions when the dynamics are translation-invariant
+//     in f0/f1 (cart position and velocity: every cart-pole environment), so a state-plane needs only a
+//     handful of V-planes: 2^(D-2) corner planes per distinct successor cell;
+//   * those V-planes are brought in by TMA bulk copies (cp.async.bulk.shared::cluster.global, one
+//     contiguous 4*PS_P-byte copy per plane, completion on an mbarrier) into PS_NS shared-memory slots.
+//     WHICH planes go into WHICH slots and WHEN is a per-policy plan computed once per policy by
+//     pi::plane_plan_kernel (plane_plan.cuh): slots are reused between consecutive state-planes
+//     (measured on K5: 16 plane loads per state-plane instead of 36), loads whose slot is idle are issued
+//     one step ahead ("early") and overlap the previous plane's backups;
+//   * a backup then reads its corners with LDS at [slot(cell, outer corner) + in-plane offset + immediate]
+//     — one shared-memory wavefront per 32 lanes instead of 2.5 L1 wavefronts per gather — and runs the
+//     reference's arithmetic unchanged: w_c = ((((f_0 f_1) f_2) ..) f_{D-1}), ev = fma(w_c, V_c, ev) for c
+//     ascending, new_V = fma(gamma, ev, reward)  =>  bit-identical V.
+//
+// A state whose successor cell could not be staged (more distinct cells in a plane than the plan
+// holds, no free slot) is flagged by the planner and gathers from global memory like gp_sweep does.
+//
+// The host prepends (dpb200.cu: plane_preamble):
+//   PS_D, PS_P, PS_NS, PS_THREADS (consumer threads = PS_P rounded up to a warp), PS_MINB, PS_L, PS_LV,
+//   PS_PACK, ps_cj[2^D] (outer-corner number of corner c), ps_imm[2^D] (in-plane float offset of corner c),
+//   gp_off[2^D] (global V offset of corner c, fallback path).
+
+typedef unsigned long long ps_u64;
+
+struct PsCtl {   // == pi::Ctl
+    int base, parity0, done, conv_sweep;
+    float last_delta, check_delta;
+    unsigned long long changed;
+    unsigned int pad[8];
+};
+struct PsPeerOut {   // == pi::PeerOut
+    int n;
+    int pad;
+    float* V0[7];
+    float* V1[7];
+    long long lo[7];
+    long long hi[7];
+};
+__device__ __forceinline__ void ps_store_peers(const PsPeerOut& po, bool out_is_V0, long long g, float v) {
+    for (int r = 0; r < po.n; ++r)
+        if (g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
+}
+
+#define PS_MAXC 8          // staged successor cells per state-plane
+#define PS_MAXOC 16        // outer corners per cell (2^(D-2), D <= 6)
+#define PS_MAXLOADS 80     // plane loads per step
+#define PS_FALLBACK 0x40000000
+
+struct PsRec {   // == pi::PlaneRec (plane_plan.cuh)
+    unsigned char n_early, n_late, n_cells, flags;
+    unsigned int pad[3];
+    unsigned short cs[PS_MAXC][PS_MAXOC];   // slot byte offset / 16 of (cell, outer corner)
+    unsigned int loads[PS_MAXLOADS];        // (slot << 24) | V-plane number; early loads first
+};
+
+struct PsParams {
+    const unsigned char* prow0;  // planned first row plane: [code, f0, f1, f2] per state (16 B)
+    const unsigned char* rows;   // the policy's rows (pi::Row<D> planes); plane 0 is read on the fallback path only
+    const PsRec* plan;           // one record per local state-plane
+    float* V0;
+    float* V1;
+    const PsCtl* ctl;
+    float* partial;              // [gridDim.x]
+    long long n_local;
+    long long n_pad;
+    long long s_begin;
+    int n_planes;                // local state-planes
+    int n_chunks;
+    float gamma;
+    int j;
+    int check;
+    PsPeerOut peers;
+};
+
+#define PS_W (PS_D + 2)
+#define PS_N4 (PS_W / 4)
+#define PS_N2 ((PS_W % 4) / 2)
+#define PS_C (1 << PS_D)
+#define PS_NOC (PS_C / 4)
+#ifndef PS_LV
+#define PS_LV 2
+#endif
+#define PS_NT (PS_C >> PS_LV)
+#define PS_PLANE_BYTES (PS_P * 4)
+#define PS_SLOTS_BYTES (PS_NS * PS_PLANE_BYTES)
+#define PS_CS_WORDS (PS_MAXC * PS_MAXOC)
+
+// ------------------------------------------------------------------ mbarrier / TMA bulk copy
+__device__ __forceinline__ unsigned ps_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ps_mbar_init(ps_u64* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ps_saddr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ps_mbar_expect(ps_u64* b, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(ps_saddr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ps_mbar_arrive_expect(ps_u64* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ps_saddr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ps_mbar_arrive(ps_u64* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ps_saddr(b)) : "memory");
+}
+__device__ __forceinline__ void ps_mbar_wait(ps_u64* b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "PS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra PS_DONE;\n\t"
+        "bra PS_WAIT;\n\t"
+        "PS_DONE:\n\t}"
+        ::"r"(ps_saddr(b)), "r"(parity) : "memory");
+}
+// one contiguous V-plane: global -> shared, completion bytes on the mbarrier
+__device__ __forceinline__ void ps_bulk_load(void* dst, const void* src, unsigned bytes, ps_u64* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ps_saddr(dst)), "l"(src), "r"(bytes), "r"(ps_saddr(b)) : "memory");
+}
+
+__device__ __forceinline__ float ps_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ ps_u64 ps_pk(float a, float b) {
+    ps_u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void ps_unpk(ps_u64 v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ ps_u64 ps_mul2(ps_u64 a, ps_u64 b) {
+    ps_u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// streaming loads of the row planes (read once per sweep)
+__device__ __forceinline__ uint4 ps_ld16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ps_ld8(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned ps_ld4(const void* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// row of local state s: word 0 = planner code (prow0), words 1..D = fractions, word D+1 = reward
+__device__ __forceinline__ void ps_load_row(const PsParams& p, long long s, unsigned (&w)[PS_W]) {
+    {
+        const uint4 v = ps_ld16(p.prow0 + (size_t)s * 16u);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+#pragma unroll
+    for (int q = 1; q < PS_N4; ++q) {
+        const uint4 v = ps_ld16(p.rows + (size_t)q * 16u * (size_t)p.n_pad + (size_t)s * 16u);
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+#if PS_N2
+    {
+        const uint2 v = ps_ld8(p.rows + (size_t)PS_N4 * 16u * (size_t)p.n_pad + (size_t)s * 8u);
+        w[4 * PS_N4] = v.x; w[4 * PS_N4 + 1] = v.y;
+    }
+#endif
+#if PS_W % 2
+    w[PS_W - 1] = ps_ld4(p.rows + ((size_t)PS_N4 * 16u + (size_t)PS_N2 * 8u) * (size_t)p.n_pad + (size_t)s * 4u);
+#endif
+}
+
+// Fallback: the successor cell of this state is not staged -> gather from global memory (gp_sweep's arithmetic).
+// Scalars by value: the row must not be forced into local memory by a call.
+__device__ __noinline__ float ps_gather_global(const float* __restrict__ Vin, int base, float f0, float f1, float f2, float f3
+#if PS_D >= 5
+                                               , float f4
+#endif
+#if PS_D >= 6
+                                               , float f5
+#endif
+) {
+    const float* v = Vin + base;
+    float ev = 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < PS_C; ++c) {
+        float leaf = (c & 1) ? f0 : 1.0f - f0;
+        leaf = leaf * ((c & 2) ? f1 : 1.0f - f1);
+        leaf = leaf * ((c & 4) ? f2 : 1.0f - f2);
+        leaf = leaf * ((c & 8) ? f3 : 1.0f - f3);
+#if PS_D >= 5
+        leaf = leaf * ((c & 16) ? f4 : 1.0f - f4);
+#endif
+#if PS_D >= 6
+        leaf = leaf * ((c & 32) ? f5 : 1.0f - f5);
+#endif
+        int off = 0;
+#pragma unroll
+        for (int d = 0; d < PS_D; ++d)
+            if ((c >> d) & 1) off += gp_off[1 << d];
+        ev = fmaf(leaf, __ldg(v + off), ev);
+    }
+    return ev;
+}
+
+#define PS_CWARPS (PS_THREADS / 32)     // consumer warps
+
+// Roles: warps 0 .. PS_CWARPS-1 back up the states of the current plane (thread t <-> state t); the last warp is the
+// PRODUCER: it issues the TMA bulk loads of the plan and publishes the slot offsets of each step.
+// Synchronisation (no CTA-wide barrier in the loop):
+//   full[b]  (tx barrier, one arrival by the producer): the V-planes and slot offsets of step `it` (b = it & 1) are in
+//            shared memory.  Early loads of step it+1 are issued — and, when that step has no late loads, the barrier
+//            is armed — while step `it` is still being computed, so a warp that finishes early runs one step ahead;
+//   done[b]  (PS_CWARPS arrivals): every consumer warp has finished step `it`: its slots may be overwritten.
+extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(const PsParams p)
+{
+    extern __shared__ __align__(128) unsigned char ps_smem[];
+    unsigned* const cs_s = reinterpret_cast<unsigned*>(ps_smem + PS_SLOTS_BYTES);                    // [2][PS_CS_WORDS] slot byte offsets
+    ps_u64* const full = reinterpret_cast<ps_u64*>(ps_smem + PS_SLOTS_BYTES + 2 * PS_CS_WORDS * 4);   // [2]
+    ps_u64* const done = full + 2;                                                                   // [2]
+    __shared__ float s_red[(PS_THREADS + 32) / 32];
+
+    const PsCtl* __restrict__ ctl = p.ctl;
+    if (ctl->done) return;
+    const int par = (ctl->base + p.j + ctl->parity0) & 1;
+    const float* __restrict__ Vin = par ? p.V1 : p.V0;
+    float* __restrict__ Vout = par ? p.V0 : p.V1;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool is_prod = tid >= PS_THREADS;
+    const bool has_state = tid < PS_P;
+
+    if (tid == 0) {
+        ps_mbar_init(&full[0], 1);
+        ps_mbar_init(&full[1], 1);
+        ps_mbar_init(&done[0], PS_CWARPS);
+        ps_mbar_init(&done[1], PS_CWARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    unsigned it = 0;   // steps this CTA has started: step `it` completes phase (it >> 1) & 1 of full[it & 1] and done[it & 1]
+    float res = 0.0f;
+
+    if (is_prod) {
+        // ------------------------------------------------------------------ producer warp
+        auto stage_cs = [&](const PsRec* r, unsigned buf) {   // slot offsets: u16 units of 16 bytes -> byte offsets
+            const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(r->cs) + lane * 4);
+            uint4 o;
+            o.x = (v.x & 0xffffu) << 4; o.y = (v.x >> 16) << 4; o.z = (v.y & 0xffffu) << 4; o.w = (v.y >> 16) << 4;
+            *reinterpret_cast<uint4*>(cs_s + buf * PS_CS_WORDS + lane * 4) = o;
+        };
+        auto copies = [&](const PsRec* r, unsigned first, unsigned n, ps_u64* bar) {
+            for (unsigned q = lane; q < n; q += 32) {
+                const unsigned e = r->loads[first + q];
+                ps_bulk_load(ps_smem + (size_t)(e >> 24) * PS_PLANE_BYTES, Vin + (size_t)(e & 0xffffffu) * PS_P, PS_PLANE_BYTES, bar);
+            }
+        };
+        bool armed = false;   // full[it & 1] was already armed one step ahead
+        for (int chunk = blockIdx.x; chunk < p.n_chunks; chunk += gridDim.x) {
+            const int pl0 = chunk * PS_L;
+            const int Lc = (p.n_planes - pl0) < PS_L ? (p.n_planes - pl0) : PS_L;
+            const PsRec* rec = p.plan + pl0;
+            for (int i = 0; i < Lc; ++i, ++it) {
+                const PsRec* r = rec + i;
+                const unsigned b = it & 1;
+                // every consumer warp is done with the previous step: its slots (and the other cs buffer) are free
+                if (it > 0) ps_mbar_wait(&done[b ^ 1], ((it - 1) >> 1) & 1);
+                if (!armed) {
+                    stage_cs(r, b);
+                    const unsigned nl = r->n_late;
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (nl) ps_mbar_arrive_expect(&full[b], nl * (unsigned)PS_PLANE_BYTES);
+                        else ps_mbar_arrive(&full[b]);
+                    }
+                    __syncwarp();
+                    copies(r, r->n_early, nl, &full[b]);
+                }
+                armed = false;
+                if (i + 1 < Lc) {
+                    const PsRec* rn = r + 1;
+                    const unsigned ne = rn->n_early, nl = rn->n_late;
+                    stage_cs(rn, b ^ 1);
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (nl == 0) {   // nothing of the next step waits for this one: arm it now, warps may run ahead
+                            if (ne) ps_mbar_arrive_expect(&full[b ^ 1], ne * (unsigned)PS_PLANE_BYTES);
+                            else ps_mbar_arrive(&full[b ^ 1]);
+                        } else if (ne) {
+                            ps_mbar_expect(&full[b ^ 1], ne * (unsigned)PS_PLANE_BYTES);
+                        }
+                    }
+                    __syncwarp();
+                    copies(rn, 0, ne, &full[b ^ 1]);
+                    armed = nl == 0;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumer warps
+        for (int chunk = blockIdx.x; chunk < p.n_chunks; chunk += gridDim.x) {
+            const int pl0 = chunk * PS_L;
+            const int Lc = (p.n_planes - pl0) < PS_L ? (p.n_planes - pl0) : PS_L;
+            unsigned w[PS_W];
+            if (has_state) ps_load_row(p, (long long)pl0 * PS_P + tid, w);
+            for (int i = 0; i < Lc; ++i, ++it) {
+                const unsigned b = it & 1;
+                const long long s = (long long)(pl0 + i) * PS_P + tid;   // local state
+                const long long g = p.s_begin + s;
+                const int code = has_state ? (int)w[0] : -1;
+                const bool staged = code >= 0 && !(code & PS_FALLBACK);
+                const unsigned k = staged ? ((unsigned)code >> 16) : 0u;
+                const unsigned ip = staged ? ((unsigned)code & 0xffffu) : 0u;
+                float fr[PS_D];
+#pragma unroll
+                for (int d = 0; d < PS_D; ++d) fr[d] = __uint_as_float(w[1 + d]);
+                const float reward = __uint_as_float(w[PS_D + 1]);
+                // the next plane's row: in flight while this plane is backed up
+                if (i + 1 < Lc && has_state) ps_load_row(p, s + PS_P, w);
+                float vold = 0.0f;
+                if (has_state && (p.check || code == -2)) vold = Vin[g];
+
+                ps_mbar_wait(&full[b], (it >> 1) & 1);
+
+                float ev = 0.0f;
+                if (staged) {
+                    const unsigned* csk = cs_s + b * PS_CS_WORDS + k * PS_MAXOC;
+                    const unsigned char* sbase = ps_smem + ip * 4u;
+#if PS_PACK
+                    // weight tree in packed pairs (corner bit 0 = the two halves): level d multiplies every pair by
+                    // (1-f_d, 1-f_d) and (f_d, f_d) — one mul.rn.f32x2 per two products, each half rounded like the
+                    // scalar product of the reference
+                    ps_u64 node[PS_NT / 2];
+                    node[0] = ps_pk(1.0f - fr[0], fr[0]);
+#pragma unroll
+                    for (int d = 1; d < PS_D - PS_LV; ++d) {
+                        const ps_u64 ff = ps_pk(fr[d], fr[d]), gg = ps_pk(1.0f - fr[d], 1.0f - fr[d]);
+#pragma unroll
+                        for (int c = PS_NT / 4 - 1; c >= 0; --c) {
+                            if (c < (1 << (d - 1))) {
+                                const ps_u64 t = node[c];
+                                node[c + (1 << (d - 1))] = ps_mul2(t, ff);
+                                node[c] = ps_mul2(t, gg);
+                            }
+                        }
+                    }
+                    ps_u64 wt[PS_LV][2];
+#pragma unroll
+                    for (int q = 0; q < PS_LV; ++q) {
+                        const float l = fr[PS_D - PS_LV + q];
+                        wt[q][0] = ps_pk(1.0f - l, 1.0f - l);
+                        wt[q][1] = ps_pk(l, l);
+                    }
+#pragma unroll
+                    for (int c = 0; c < PS_C; c += 2) {
+                        ps_u64 leaf = node[(c & (PS_NT - 1)) >> 1];
+#pragma unroll
+                        for (int q = 0; q < PS_LV; ++q) leaf = ps_mul2(leaf, wt[q][(c >> (PS_D - PS_LV + q)) & 1]);
+                        float l0, l1;
+                        ps_unpk(leaf, l0, l1);
+                        const float* a0 = reinterpret_cast<const float*>(sbase + csk[ps_cj[c]]);
+                        const float* a1 = reinterpret_cast<const float*>(sbase + csk[ps_cj[c + 1]]);
+                        ev = fmaf(l0, a0[ps_imm[c]], ev);
+                        ev = fmaf(l1, a1[ps_imm[c + 1]], ev);
+                    }
+#else
+                    float pre[PS_NT];
+                    pre[0] = 1.0f - fr[0];
+                    pre[1] = fr[0];
+#pragma unroll
+                    for (int d = 1; d < PS_D - PS_LV; ++d) {
+                        const float f = fr[d], gq = 1.0f - f;
+#pragma unroll
+                        for (int c = PS_NT / 2 - 1; c >= 0; --c) {
+                            if (c < (1 << d)) {
+                                const float t = pre[c];
+                                pre[c + (1 << d)] = t * f;
+                                pre[c] = t * gq;
+                            }
+                        }
+                    }
+                    float wt[PS_LV][2];
+#pragma unroll
+                    for (int q = 0; q < PS_LV; ++q) {
+                        const float l = fr[PS_D - PS_LV + q];
+                        wt[q][0] = 1.0f - l;
+                        wt[q][1] = l;
+                    }
+#pragma unroll
+                    for (int c = 0; c < PS_C; ++c) {
+                        float leaf = pre[c & (PS_NT - 1)];
+#pragma unroll
+                        for (int q = 0; q < PS_LV; ++q) leaf = leaf * wt[q][(c >> (PS_D - PS_LV + q)) & 1];
+                        const float* a = reinterpret_cast<const float*>(sbase + csk[ps_cj[c]]);
+                        ev = fmaf(leaf, a[ps_imm[c]], ev);
+                    }
+#endif
+                } else if (code >= 0) {
+                    // not staged: the original base index is word 0 of the policy's row
+                    const int base = (int)ps_ld4(p.rows + (size_t)s * 16u);
+                    ev = ps_gather_global(Vin, base, fr[0], fr[1], fr[2], fr[3]
+#if PS_D >= 5
+                                          , fr[4]
+#endif
+#if PS_D >= 6
+                                          , fr[5]
+#endif
+                    );
+                }
+                if (has_state) {
+                    const float vnew = code == -2 ? vold : fmaf(p.gamma, ev, reward);
+                    Vout[g] = vnew;
+                    if (p.peers.n) ps_store_peers(p.peers, par != 0, g, vnew);
+                    if (p.check) res = fmaxf(res, fabsf(vnew - vold));
+                }
+                __syncwarp();
+                if (lane == 0) ps_mbar_arrive(&done[b]);
+            }
+        }
+    }
+
+    if (!p.check) return;
+    res = ps_warp_max(res);
+    if (lane == 0) s_red[tid >> 5] = res;
+    __syncthreads();
+    if (tid < 32) {
+        float r = tid < (PS_THREADS + 32) / 32 ? s_red[tid] : 0.0f;
+        r = ps_warp_max(r);
+        if (tid == 0) p.partial[blockIdx.x] = r;
+    }
+}

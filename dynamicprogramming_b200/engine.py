@@ -453,7 +453,10 @@ class _CudaPolicyIterationBase(abc.ABC):
         lines = (C.c_double * _ffi.PI_MAX_DIMS)()
         _ffi.check(_ffi.lib().pi_layout(self._engine, C.byref(fast), perm, lines))
         D = self.N_DIMS
-        return {"fast_dim": int(fast.value), "perm": [int(perm[k]) for k in range(D)],
+        p = [int(perm[k]) for k in range(D)]
+        # two fast dimensions (a "plane" layout for the plane-staged sweep) when the slower ones are not in logical order
+        rest = [d for d in range(D) if d != p[-1]]
+        return {"fast_dim": int(fast.value), "fast_dim2": p[-2] if D >= 2 and p[:-1] != rest else -1, "perm": p,
                 "probe_lines": [float(lines[d]) for d in range(D)]}
 
     def lookup_actions(self, states: np.ndarray) -> np.ndarray:
@@ -482,8 +485,21 @@ class _CudaPolicyIterationBase(abc.ABC):
         buf = C.create_string_buffer(256)
         ms_s, ms_x = C.c_double(), C.c_double()
         kind = _ffi.lib().pi_eval_kernel_info(self._engine, buf, 256, C.byref(ms_s), C.byref(ms_x))
-        return {"xline": kind == 1, "kernel": buf.value.decode(), "probe_ms_scalar": ms_s.value,
+        return {"xline": kind == 1, "plane": kind == 2, "kernel": buf.value.decode(), "probe_ms_scalar": ms_s.value,
                 "probe_ms_selected": ms_x.value}
+
+    def debug_plane(self, cfg: str = "", iters: int = 5) -> dict:
+        """Test hook: the plane-staged sweep configuration `cfg` ("NS,L,minb,lv,pack", 0 = default) vs the kernel
+        the engine currently runs, on the current rows and V; timings, plan statistics and the number of
+        differing V words (must be 0)."""
+        ms_new, ms_base = C.c_float(), C.c_float()
+        mism, st, info = C.c_int64(), (C.c_double * 4)(), (C.c_int32 * 6)()
+        _ffi.check(_ffi.lib().pi_debug_plane(self._engine, cfg.encode(), int(iters), C.byref(ms_new), C.byref(ms_base),
+                                             C.byref(mism), st, info))
+        return {"ms_plane": ms_new.value, "ms_base": ms_base.value, "mismatches": int(mism.value),
+                "loads_per_plane": st[0], "late_per_plane": st[1], "cells_per_plane": st[2], "fallback_frac": st[3],
+                "registers": int(info[0]), "grid": int(info[1]), "block": int(info[2]), "smem": int(info[3]),
+                "slots": int(info[4]), "chunk": int(info[5])}
 
     def debug_xline(self, cfg: str, iters: int = 5) -> dict:
         """Test hook: run the x-line sweep configuration `cfg` and the scalar sweep on the current

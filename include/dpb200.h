@@ -227,6 +227,15 @@ int pi_xline_compile_check(int32_t n_dims, int32_t bins, const char* cfg, int64_
 int pi_debug_xline(pi_engine* e, const char* cfg, int32_t iters, float* ms_xline, float* ms_scalar,
                    int64_t* mismatches, double* window_fraction, int32_t* info);
 
+/* Test hook for the plane-staged sweep (csrc/plane_sweep_src.cuh: V read from shared memory, V-planes staged by TMA
+ * bulk copies after a per-policy plan, csrc/plane_plan.cuh): compiles configuration `cfg` = "NS,L,minb,lv,pack"
+ * (slots, state-planes per chunk, CTAs per SM, lean weight-tree levels, packed f32x2 weight tree; 0 = default),
+ * plans the current rows, runs it and the engine's currently selected kernel `iters` times on the current rows and V
+ * and counts differing words (must be 0).  stats = {plane loads, late loads, cells per state-plane, fraction of states
+ * not staged}; info = {registers, grid, block, shared-memory bytes, slots, chunk}.  Engine state unchanged. */
+int pi_debug_plane(pi_engine* e, const char* cfg, int32_t iters, float* ms_plane, float* ms_base, int64_t* mismatches,
+                   double* stats, int32_t* info);
+
 /* Test hook for the JIT sweeps of csrc/pair_sweep_src.cuh (grid strides as immediates): compiles the
  * configuration (threads per block, blocks per SM, lean weight-tree levels 1..3, gathers per explicitly
  * scheduled group or 0, single = 1: one state per thread / 0: two states per thread with packed f32x2
