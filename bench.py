@@ -48,6 +48,23 @@ METRIC = "bellman_state_backups_per_s"
 UNIT = "backups/s"
 
 
+def workload_config(bins: int, n_actions: int, gamma: float, sharding: str) -> dict:
+    """`config` of the JSON line — the same keys and (at N = 1) the same values in both arms."""
+    N = bins ** 6
+    return {"workload": f"{ENV} 6-D --bins {bins} ({N:,} states x {n_actions} actions), "
+                        f"policy evaluation, step = {SWEEPS_PER_STEP} Jacobi sweeps (one reference sync interval)",
+            "policy": "greedy policy after PI iteration 1", "gamma": gamma, "sharding": sharding,
+            "l2": "inputs larger than L2 (rows %.2f GB + V %.2f GB per sweep)" % (8 * 4 * N / 1e9, 4 * N / 1e9)}
+
+
+def v_checksum(t) -> int:
+    """Order-independent 64-bit checksum of a float32 device tensor: sum of its words as unsigned integers
+    (reduced on the device).  Equal checksums in both arms / at every N <=> the same multiset of V bits."""
+    import torch
+
+    return int((t.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF).sum().item())
+
+
 def _quiet_logs() -> None:
     try:
         from loguru import logger
@@ -152,6 +169,7 @@ def run_ours(args) -> dict:
     eng.sweeps(2 * SWEEPS_PER_STEP)
     eng.policy_improvement()
     build_ms = eng.engine_stats()["build_ms"]
+    improve_ms = eng.engine_stats()["improve_ms"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -181,6 +199,13 @@ def run_ours(args) -> dict:
         dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
     value = N * SWEEPS_PER_STEP / (ms_per_step * 1e-3)
+    # checksum of V after 2 x 25 + (warmup + steps) x 25 sweeps: the same point of the same protocol in the reference arm
+    v_local = torch.as_tensor(eng.d_value_function, device=f"cuda:{local}")[lo:hi]
+    csum = torch.tensor([v_checksum(v_local)], device="cuda", dtype=torch.int64)
+    if td is not None:
+        td.all_reduce(csum, op=td.ReduceOp.SUM)
+    csum = int(csum.item())
+    n_sweeps_at_checksum = 2 * SWEEPS_PER_STEP + (max(args.warmup, 3) + args.steps) * SWEEPS_PER_STEP
     kinfo = eng.eval_kernel_info()   # which sweep kernel the engine runs for THIS policy (scalar gather / x-line)
 
     # ---- end-to-end arm: host buffers in, host buffers out ---------------------
@@ -221,14 +246,11 @@ def run_ours(args) -> dict:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{ENV} 6-D --bins {args.bins} ({N:,} states x {eng.n_actions} actions), "
-                                   f"policy evaluation, step = {SWEEPS_PER_STEP} Jacobi sweeps (one reference sync interval)",
-                       "policy": "greedy policy after PI iteration 1", "gamma": eng.config.gamma,
-                       "sharding": ("contiguous state ranges, needs-driven V exchange: " + os.environ.get("DPB200_EXCHANGE", "p2p") +
-                                    " (p2p = peer stores fused into the sweep kernel over CUDA IPC / NVLink + barrier kernel; nccl = grouped send/recv)")
-                       if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (rows %.2f GB + V %.2f GB per sweep)" % (
-                           (D + 2) * 4 * N / 1e9, 4 * N / 1e9)},
+            "config": workload_config(args.bins, eng.n_actions, eng.config.gamma,
+                                      ("contiguous state ranges, needs-driven V exchange: " + os.environ.get("DPB200_EXCHANGE", "p2p") +
+                                       " (p2p = peer stores fused into the sweep kernel over CUDA IPC / NVLink + barrier kernel; nccl = grouped send/recv)")
+                                      if world > 1 else "single GPU"),
+            "v_checksum": csum, "v_checksum_after_sweeps": n_sweeps_at_checksum,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 4),
                     "d2h_bytes_per_step": int(n_local * 4 + 4),
                     "call": "pi_upload_policy_local + pi_sweeps(25) + pi_copy_local_results (pinned host buffers, each rank its own slice)"},
@@ -244,8 +266,23 @@ def run_ours(args) -> dict:
                             "bytes": int(lib.pi_table_bytes(eng._engine))},
             "wall_s_timed_region": wall_s,
         }
+        W = D + 2
+        out["stages"] = {"K5": {
+            "config": f"{ENV} --bins {args.bins}",
+            "build": stage(build_ms, (hi - lo) * eng.n_actions, W * 4, "rows"),
+            "eval": stage(ms_per_step / SWEEPS_PER_STEP, hi - lo, W * 4 + 8, "backups"),
+            "improve": stage(improve_ms, hi - lo, eng.n_actions * W * 4 + W * 4 + 8, "states"),
+            "per_gpu": world > 1}}
     eng.close()
+    # K5 run to a stable policy through the public API (every rank takes part when sharded)
+    if not args.no_stable:
+        st = run_to_stable(ENV, args.bins, local, pdist.make_shard(local) if world > 1 else None)
+        if rank == 0:
+            out["k5_to_stable"] = st
     if rank == 0:
+        if not args.no_extras and world == 1:
+            out["stages"].update(small_config_stages())
+            out["k5_bins12_to_stable"] = run_to_stable(ENV, 12, local, None)
         # K1 first: the OpenMP workers of the CPU baseline keep spinning for a while after their last
         # parallel region and would be charged to the small-grid run (host-side latency matters there)
         if not args.no_converge and world == 1:
@@ -256,6 +293,95 @@ def run_ours(args) -> dict:
         td.barrier()
         td.destroy_process_group()
     return out
+
+
+def stage(ms: float, units: int, bytes_per_unit: int, unit: str) -> dict:
+    """One stage of one configuration: device time, throughput, algorithmic HBM bytes and roofline fraction."""
+    peak, _ = measured_peak()
+    gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    return {"ms": ms, f"{unit}_per_s": units / (ms * 1e-3) if ms > 0 else 0.0, "algorithmic_bytes_per_unit": bytes_per_unit,
+            "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+
+
+# BASELINE.json configs[0..3]; K2 also with the fine action grid its description names (201 actions)
+SMALL_CONFIGS = [
+    ("K1", "pendulum", 200, None),
+    ("K2", "continuous_mountain_car", 400, None),
+    ("K2-fine", "continuous_mountain_car", 400, 201),
+    ("K3", "cartpole", 30, None),
+    ("K4", "double_pendulum_swingup", 50, None),
+]
+
+
+def small_config_stages() -> dict:
+    """Per configuration K1-K4 and per stage (table build / evaluation sweep / improvement pass): device ms, throughput,
+    algorithmic bytes, fraction of the HBM roofline — and the reference's own kernels for the same stage beside it
+    (oracle/_ref cubins; eval = its evaluation kernel + max|x-y| reduction per sweep)."""
+    import torch
+
+    from dynamicprogramming_b200 import envs
+    from oracle import ref_runner
+
+    out = {}
+    for tag, env, bins, n_act in SMALL_CONFIGS:
+        spec = envs.REGISTRY[env]
+        actions = None
+        if n_act is not None:
+            actions = np.linspace(float(spec.actions.min()), float(spec.actions.max()), n_act).astype(np.float32)
+        eng = spec.make(bins=bins, actions=actions)
+        eng.build_table()
+        eng.sweeps(2 * SWEEPS_PER_STEP)
+        eng.policy_improvement()                       # a mixed policy, as in the K5 protocol
+        st0 = eng.engine_stats()
+        eng.sweeps(8 * SWEEPS_PER_STEP)               # warm
+        _, ms = eng.sweeps(40 * SWEEPS_PER_STEP)
+        eng.policy_improvement()
+        st1 = eng.engine_stats()
+        N, A, W = eng.n_states, eng.n_actions, eng.N_DIMS + 2
+        rec = {"config": f"{env} --bins {bins}, {A} actions, {N:,} states", "kernel": eng.eval_kernel_info()["kernel"],
+               "build": stage(st1["build_ms"], N * A, W * 4, "rows"),
+               "eval": stage(ms / (40 * SWEEPS_PER_STEP), N, W * 4 + 8, "backups"),
+               "improve": stage(st1["improve_ms"] - st0["improve_ms"], N, A * W * 4 + W * 4 + 8, "states")}
+        eng.close()
+        if ref_runner.available(env):
+            ref = ref_runner.from_engine_env(env, bins=bins, actions=actions)
+            for _ in range(2 * SWEEPS_PER_STEP):
+                ref.eval_launch()
+                ref.d_value_function, ref.d_new_value_function = ref.d_new_value_function, ref.d_value_function
+            ref.improve_launch()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            n = 4 * SWEEPS_PER_STEP
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                ref.eval_launch()
+                ref._max_abs_diff()
+                ref.d_value_function, ref.d_new_value_function = ref.d_new_value_function, ref.d_value_function
+            e1.record()
+            ref.improve_launch()
+            e2.record()
+            torch.cuda.synchronize()
+            rec["reference_kernels"] = {"eval_ms_per_sweep": e0.elapsed_time(e1) / n, "improve_ms": e1.elapsed_time(e2)}
+            del ref
+            torch.cuda.empty_cache()
+        out[tag] = rec
+    return out
+
+
+def run_to_stable(env: str, bins: int, device: int, shard) -> dict:
+    """run() to a stable policy through the public API: table build, every evaluation and improvement, D2H."""
+    from dynamicprogramming_b200 import envs
+
+    spec = envs.REGISTRY[env]
+    t0 = time.perf_counter()
+    eng = spec.make(bins=bins, device=device, shard=shard)
+    t1 = time.perf_counter()
+    eng.run()
+    t2 = time.perf_counter()
+    return {"workload": f"{env} --bins {bins} ({eng.n_states:,} states x {eng.n_actions} actions), run() to a stable policy "
+                        "incl. table build and D2H", "seconds": t2 - t1, "create_seconds": t1 - t0,
+            "pi_iterations": eng.pi_iterations, "eval_sweeps": eng.total_eval_sweeps, "converged": bool(eng.converged),
+            "eval_ms": eng.stats["eval_ms"], "improve_ms": eng.stats["improve_ms"], "build_ms": eng.stats["build_ms"]}
 
 
 def cpu_baseline(bins: int, budget_s: float = 12.0) -> dict:
@@ -303,6 +429,8 @@ def time_to_converge() -> dict:
     dt = time.perf_counter() - t0
     return {"workload": "pendulum 2-D --bins 200 (40,000 states x 21 actions), run() incl. table build and D2H",
             "seconds": dt, "pi_iterations": eng.pi_iterations, "eval_sweeps": eng.total_eval_sweeps,
+            "converged": bool(eng.converged),
+            "note": "the policy keeps changing until max_pi_iter = 50 in both arms (same counts as the reference loop)",
             "eval_ms": eng.stats["eval_ms"], "improve_ms": eng.stats["improve_ms"]}
 
 
@@ -318,8 +446,8 @@ def run_reference(args) -> dict | None:
 
     spec = envs.REGISTRY[ENV]
     N = args.bins ** 6
-    cfg_desc = {"workload": f"{ENV} 6-D --bins {args.bins} ({N:,} states x {len(spec.actions)} actions), "
-                            f"policy evaluation, step = {SWEEPS_PER_STEP} Jacobi sweeps (one reference sync interval)"}
+    cfg_desc = workload_config(args.bins, len(spec.actions), spec.config().gamma, "single GPU")
+    csum = None
     if ref_runner.available(ENV) and torch.cuda.is_available():
         torch.cuda.set_device(0)
         ref = ref_runner.from_engine_env(ENV, bins=args.bins)
@@ -348,6 +476,15 @@ def run_reference(args) -> dict | None:
         torch.cuda.synchronize()
         ms_per_step = e0.elapsed_time(e1) / args.steps
         value = N * SWEEPS_PER_STEP / (ms_per_step * 1e-3)
+        csum = v_checksum(ref.d_value_function)
+        e2 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        ref.improve_launch()
+        e2.record()
+        torch.cuda.synchronize()
+        ref_stages = {"K5": {"eval_ms_per_sweep": ms_per_step / SWEEPS_PER_STEP, "improve_ms": e1.elapsed_time(e2)}}
+        del ref
+        torch.cuda.empty_cache()
         # K1 (pendulum --bins 200) to the end with the reference's kernels and host loop, like our arm's
         # time_to_converge: run() only (kernels are already compiled on both sides), D2H included
         ttc = None
@@ -357,7 +494,19 @@ def run_reference(args) -> dict | None:
             t0 = time.perf_counter()
             ref1.run()
             ttc = {"workload": "pendulum 2-D --bins 200 (40,000 states x 21 actions), reference kernels + reference host loop, run() incl. D2H",
-                   "seconds": time.perf_counter() - t0, "pi_iterations": ref1.pi_iterations, "eval_sweeps": ref1.total_sweeps}
+                   "seconds": time.perf_counter() - t0, "pi_iterations": ref1.pi_iterations, "eval_sweeps": ref1.total_sweeps,
+                   "converged": bool(ref1.converged)}
+        k5_12 = None
+        if not args.no_extras:
+            # the autoresearch trial workload (runners/trial_runner.sh: --bins 12) to a stable policy with the reference's
+            # kernels and host loop
+            ref12 = ref_runner.from_engine_env(ENV, bins=12)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref12.run()
+            k5_12 = {"workload": f"{ENV} --bins 12 ({ref12.n_states:,} states), reference kernels + reference host loop, run() incl. D2H",
+                     "seconds": time.perf_counter() - t0, "pi_iterations": ref12.pi_iterations, "eval_sweeps": ref12.total_sweeps,
+                     "converged": bool(ref12.converged)}
         kind = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                 "sample": "the reference's own eval kernel + max|x-y| reduction (oracle/_ref cubin, NVRTC-compiled "
                           "from /root/reference) on one B200, full grid; the reference has no CPU path"}
@@ -367,12 +516,21 @@ def run_reference(args) -> dict | None:
         ms_per_step = N * SWEEPS_PER_STEP / value * 1e3
         kind = dict(cb)
         ttc = None
+        k5_12 = None
+        ref_stages = None
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc, "cpu_baseline": kind,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if csum is not None:
+        out["v_checksum"] = csum
+        out["v_checksum_after_sweeps"] = 2 * SWEEPS_PER_STEP + (max(args.warmup, 3) + args.steps) * SWEEPS_PER_STEP
     if ttc is not None:
         out["time_to_converge"] = ttc
+    if k5_12 is not None:
+        out["k5_bins12_to_stable"] = k5_12
+    if ref_stages is not None:
+        out["stages"] = ref_stages
     return out
 
 
@@ -385,6 +543,8 @@ def main() -> int:
     ap.add_argument("--bins", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-converge", action="store_true")
+    ap.add_argument("--no-stable", action="store_true", help="skip the K5 run to a stable policy")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-configuration stage table (K1-K4) and the --bins 12 runs")
     args = ap.parse_args()
     _quiet_logs()
     # stdout carries exactly ONE JSON line: while the benchmark runs, file descriptor 1 points at stderr, so

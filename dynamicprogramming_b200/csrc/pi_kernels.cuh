@@ -113,13 +113,15 @@ struct BarrierParams {
     unsigned* flags_peer[kMaxPeers + 1];   // indexed by rank; [own rank] unused
     unsigned* epoch;                       // local sweep counter
     unsigned* err;
+    Ctl* ctl;                              // a timeout also sets ctl->done: the remaining sweeps of the batch become no-ops
+    long long timeout_ticks;               // clock64 ticks a rank waits for a peer (DPB200_BARRIER_TIMEOUT_S, default 120 s)
     int rank;
     int world;
 };
 __global__ void xgpu_barrier_kernel(const BarrierParams b) {
     const int t = threadIdx.x;
     const unsigned e = *b.epoch + 1;
-    if (*b.err) return;   // a barrier already timed out: do not wait again, the host reports PI_ERR_COMM
+    if (*b.err) return;   // a barrier already timed out in this call: do not wait again, the host reports PI_ERR_COMM
     if (t < b.world && t != b.rank) {
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags_peer[t] + b.rank), "r"(e) : "memory");
@@ -128,7 +130,11 @@ __global__ void xgpu_barrier_kernel(const BarrierParams b) {
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(b.flags_local + t) : "memory");
             if ((int)(seen - e) >= 0) break;
-            if (clock64() - t0 > 20000000000LL) { *b.err = 1u; break; }   // ~10 s at 2 GHz
+            if (clock64() - t0 > b.timeout_ticks) {   // never compute on stale halo values
+                *b.err = 1u;
+                b.ctl->done = 1;
+                break;
+            }
         } while (true);
     }
     __syncthreads();

@@ -51,6 +51,7 @@ struct PlanParams {
     int P;                       // states per plane
     int NS;                      // shared-memory slots of the sweep
     int noc;                     // outer corners per cell
+    int pitch;                   // floats between slots in shared memory (>= P, multiple of 4)
     int ooff[kPlanMaxOC];        // V-plane offset of outer corner j
 };
 
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kPlanThreads) plane_plan_kernel(const PlanPara
             const int k = tid / kPlanMaxOC, j = tid - k * kPlanMaxOC;
             int slot = 0;
             if (k < K && j < q.noc && !cell_bad[k]) slot = cs[k][j];
-            rec->cs[k][j] = (unsigned short)(((size_t)slot * (size_t)q.P * 4u) >> 4);
+            rec->cs[k][j] = (unsigned short)(((size_t)slot * (size_t)q.pitch * 4u) >> 4);
         }
         for (int t = tid; t < n_early + n_late; t += kPlanThreads) rec->loads[t] = t < n_early ? early[t] : late[t - n_early];
         unsigned n_fb = 0, n_live = 0;

@@ -91,7 +91,10 @@ struct PsParams {
 #endif
 #define PS_NT (PS_C >> PS_LV)
 #define PS_PLANE_BYTES (PS_P * 4)
-#define PS_SLOTS_BYTES (PS_NS * PS_PLANE_BYTES)
+#ifndef PS_PITCH
+#define PS_PITCH PS_PLANE_BYTES      // bytes between slots (>= PS_PLANE_BYTES, multiple of 16)
+#endif
+#define PS_SLOTS_BYTES (PS_NS * PS_PITCH)
 #define PS_CS_WORDS (PS_MAXC * PS_MAXOC)
 
 // ------------------------------------------------------------------ mbarrier / TMA bulk copy
@@ -257,17 +260,26 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
 
     if (is_prod) {
         // ------------------------------------------------------------------ producer warp
-        auto stage_cs = [&](const PsRec* r, unsigned buf) {   // slot offsets: u16 units of 16 bytes -> byte offsets
-            const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(r->cs) + lane * 4);
+        // The producer is idle while the consumers compute: it fetches the plan entries of its NEXT trigger into
+        // registers before it waits for the consumers, so the TMA copies go out the moment the slots are free.
+        constexpr int kPerLane = (PS_MAXLOADS + 31) / 32;
+        auto fetch = [&](const PsRec* r, unsigned first, unsigned n, unsigned (&e)[kPerLane]) {
+#pragma unroll
+            for (int q = 0; q < kPerLane; ++q) e[q] = (unsigned)(lane + 32 * q) < n ? r->loads[first + lane + 32 * q] : 0u;
+        };
+        auto copies = [&](const unsigned (&e)[kPerLane], unsigned n, ps_u64* bar) {
+#pragma unroll
+            for (int q = 0; q < kPerLane; ++q)
+                if ((unsigned)(lane + 32 * q) < n)
+                    ps_bulk_load(ps_smem + (size_t)(e[q] >> 24) * PS_PITCH, Vin + (size_t)(e[q] & 0xffffffu) * PS_P, PS_PLANE_BYTES, bar);
+        };
+        auto stage_cs_regs = [&](const uint2 v, unsigned buf) {
             uint4 o;
             o.x = (v.x & 0xffffu) << 4; o.y = (v.x >> 16) << 4; o.z = (v.y & 0xffffu) << 4; o.w = (v.y >> 16) << 4;
             *reinterpret_cast<uint4*>(cs_s + buf * PS_CS_WORDS + lane * 4) = o;
         };
-        auto copies = [&](const PsRec* r, unsigned first, unsigned n, ps_u64* bar) {
-            for (unsigned q = lane; q < n; q += 32) {
-                const unsigned e = r->loads[first + q];
-                ps_bulk_load(ps_smem + (size_t)(e >> 24) * PS_PLANE_BYTES, Vin + (size_t)(e & 0xffffffu) * PS_P, PS_PLANE_BYTES, bar);
-            }
+        auto fetch_cs = [&](const PsRec* r) {
+            return *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(r->cs) + lane * 4);
         };
         bool armed = false;   // full[it & 1] was already armed one step ahead
         for (int chunk = blockIdx.x; chunk < p.n_chunks; chunk += gridDim.x) {
@@ -276,37 +288,50 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
             const PsRec* rec = p.plan + pl0;
             for (int i = 0; i < Lc; ++i, ++it) {
                 const PsRec* r = rec + i;
+                const PsRec* rn = r + 1;
+                const bool more = i + 1 < Lc;
                 const unsigned b = it & 1;
+                // everything this trigger needs, fetched before the wait
+                unsigned e_late[kPerLane], e_early[kPerLane];
+                unsigned nl = 0, ne_n = 0, nl_n = 0;
+                uint2 cs_cur = make_uint2(0u, 0u), cs_nxt = make_uint2(0u, 0u);
+                if (!armed) {
+                    nl = r->n_late;
+                    fetch(r, r->n_early, nl, e_late);
+                    cs_cur = fetch_cs(r);
+                }
+                if (more) {
+                    ne_n = rn->n_early; nl_n = rn->n_late;
+                    fetch(rn, 0, ne_n, e_early);
+                    cs_nxt = fetch_cs(rn);
+                }
                 // every consumer warp is done with the previous step: its slots (and the other cs buffer) are free
                 if (it > 0) ps_mbar_wait(&done[b ^ 1], ((it - 1) >> 1) & 1);
                 if (!armed) {
-                    stage_cs(r, b);
-                    const unsigned nl = r->n_late;
+                    stage_cs_regs(cs_cur, b);
                     __syncwarp();
                     if (lane == 0) {
                         if (nl) ps_mbar_arrive_expect(&full[b], nl * (unsigned)PS_PLANE_BYTES);
                         else ps_mbar_arrive(&full[b]);
                     }
                     __syncwarp();
-                    copies(r, r->n_early, nl, &full[b]);
+                    copies(e_late, nl, &full[b]);
                 }
                 armed = false;
-                if (i + 1 < Lc) {
-                    const PsRec* rn = r + 1;
-                    const unsigned ne = rn->n_early, nl = rn->n_late;
-                    stage_cs(rn, b ^ 1);
+                if (more) {
+                    stage_cs_regs(cs_nxt, b ^ 1);
                     __syncwarp();
                     if (lane == 0) {
-                        if (nl == 0) {   // nothing of the next step waits for this one: arm it now, warps may run ahead
-                            if (ne) ps_mbar_arrive_expect(&full[b ^ 1], ne * (unsigned)PS_PLANE_BYTES);
+                        if (nl_n == 0) {   // nothing of the next step waits for this one: arm it now, warps may run ahead
+                            if (ne_n) ps_mbar_arrive_expect(&full[b ^ 1], ne_n * (unsigned)PS_PLANE_BYTES);
                             else ps_mbar_arrive(&full[b ^ 1]);
-                        } else if (ne) {
-                            ps_mbar_expect(&full[b ^ 1], ne * (unsigned)PS_PLANE_BYTES);
+                        } else if (ne_n) {
+                            ps_mbar_expect(&full[b ^ 1], ne_n * (unsigned)PS_PLANE_BYTES);
                         }
                     }
                     __syncwarp();
-                    copies(rn, 0, ne, &full[b ^ 1]);
-                    armed = nl == 0;
+                    copies(e_early, ne_n, &full[b ^ 1]);
+                    armed = nl_n == 0;
                 }
             }
         }

@@ -90,8 +90,24 @@ class DeviceArray:
         import torch
         return torch.as_tensor(self, device=f"cuda:{self._owner._device}")
 
-    def get(self) -> np.ndarray:
+    def raw(self) -> np.ndarray:
+        """The buffer as the engine stores it (internal storage order, see `layout()`)."""
         return self.torch().cpu().numpy()
+
+    def get(self) -> np.ndarray:
+        """Host copy in REFERENCE order — what `cupy_array.get()` returns on the reference object.  The engine may
+        store states with other dimensions fastest (pi_layout); full-grid buffers are put back into reference order
+        here, shard-local buffers of a sharded run cannot be and raise."""
+        a = self.raw()
+        eng = self._owner
+        perm = eng.layout()["perm"]
+        if perm == list(range(eng.N_DIMS)):
+            return a
+        if a.shape != (eng.n_states,):
+            raise RuntimeError("this buffer holds one shard in the engine's storage order; use download() for reference order")
+        shape_int = [int(eng.grid_shape[d]) for d in perm]
+        inv = [perm.index(d) for d in range(eng.N_DIMS)]
+        return np.ascontiguousarray(a.reshape(shape_int).transpose(inv)).ravel()
 
 
 class _CudaPolicyIterationBase(abc.ABC):
@@ -286,12 +302,14 @@ class _CudaPolicyIterationBase(abc.ABC):
         """The complete policy-iteration loop (same for/else semantics as :357-370)."""
         self.total_eval_sweeps = 0
         self.pi_iterations = 0
+        self.converged = False
         for n in range(self.config.max_pi_iter):
             logger.info(f"-- PI Iteration {n + 1}/{self.config.max_pi_iter} --")
             self.policy_evaluation()
             self.total_eval_sweeps += self.last_eval_sweeps
             self.pi_iterations = n + 1
             if self.policy_improvement():
+                self.converged = True
                 logger.success(f"Policy Iteration converged at iteration {n + 1}.")
                 break
         else:
@@ -475,7 +493,8 @@ class _CudaPolicyIterationBase(abc.ABC):
         if look is None or look[0] is not self.policy:
             if look is not None:
                 look[1].close()
-            look = (self.policy, PolicyLookup(self.policy, self.action_space, self.bounds_low, self.bounds_high, self.grid_shape))
+            look = (self.policy, PolicyLookup(self.policy, self.action_space, self.bounds_low, self.bounds_high, self.grid_shape,
+                                              device=int(getattr(self, "_device", os.environ.get("LOCAL_RANK", 0)))))
             self._lookup = look
         return look[1](pts)
 

@@ -66,16 +66,42 @@ class PolicyLookup:
 _cache: dict = {}
 
 
-def get_optimal_action(state, policy, action_space, bounds_low, bounds_high, grid_shape, strides=None, corner_bits=None):
+def _fingerprint(policy, action_space, bounds_low, bounds_high, grid_shape) -> tuple:
+    """Cheap content check of everything the device table was built from: the grid, the action values and a strided
+    sample + checksum of the policy (an in-place policy update or a recycled id() must not return stale actions)."""
+    pol = np.asarray(policy)
+    flat = pol.ravel()
+    step = max(1, flat.size // 4096)
+    return (tuple(int(x) for x in np.asarray(grid_shape).ravel()),
+            np.asarray(bounds_low, dtype=np.float32).tobytes(), np.asarray(bounds_high, dtype=np.float32).tobytes(),
+            np.asarray(action_space, dtype=np.float32).tobytes(), flat.size, flat[::step].tobytes(),
+            int(flat.sum(dtype=np.int64)))
+
+
+def invalidate_lookup_cache() -> None:
+    """Drop every cached device table of get_optimal_action."""
+    while _cache:
+        _cache.popitem()[1][3].close()
+
+
+def get_optimal_action(state, policy, action_space, bounds_low, bounds_high, grid_shape, strides=None, corner_bits=None,
+                       device: int | None = None):
     """Drop-in for utils.barycentric.get_optimal_action (same arguments; `strides` and `corner_bits`
-    are implied by `grid_shape` and accepted for compatibility).  Accepts one state or a batch; the
-    device table is cached per (policy, action_space) object pair."""
-    key = (id(policy), id(action_space))
+    are implied by `grid_shape` and accepted for compatibility).  Accepts one state or a batch.  The device table is
+    cached per (policy, action_space) object pair and revalidated on every call against a fingerprint of the policy,
+    the action values and the grid; `device` defaults to LOCAL_RANK (0 outside torchrun)."""
+    import os
+
+    dev = int(os.environ.get("LOCAL_RANK", 0)) if device is None else int(device)
+    key = (id(policy), id(action_space), dev)
+    fp = _fingerprint(policy, action_space, bounds_low, bounds_high, grid_shape)
     hit = _cache.get(key)
-    if hit is None or hit[0] is not policy:
+    if hit is None or hit[0] is not policy or hit[1] is not action_space or hit[2] != fp:
+        if hit is not None:
+            _cache.pop(key)[3].close()
         if len(_cache) >= 4:
-            _cache.pop(next(iter(_cache)))[1].close()
-        hit = (policy, PolicyLookup(policy, action_space, bounds_low, bounds_high, grid_shape))
+            _cache.pop(next(iter(_cache)))[3].close()
+        hit = (policy, action_space, fp, PolicyLookup(policy, action_space, bounds_low, bounds_high, grid_shape, device=dev))
         _cache[key] = hit
-    out = hit[1](state)
+    out = hit[3](state)
     return out[0] if np.ndim(state) == 1 else out

@@ -12,7 +12,8 @@ cupy is not installed in this image, so the three things cupy does for the
 reference are done here with torch + the CUDA driver API through ctypes:
   * device arrays              -> torch tensors (legacy default stream)
   * RawModule / get_function   -> cuModuleLoadData / cuModuleGetFunction
-  * ReductionKernel max|x-y|   -> torch (exact: max and abs do not round)
+  * ReductionKernel max|x-y|   -> oracle_max_abs_diff, a one-pass fused reduction compiled into the same
+                                  cubin (exact: max and abs do not round); torch ops only when an old cubin lacks it
 The kernel launches use the reference's launch shape: 256 threads per block,
 ceil(N/256) blocks (src/cuda_policy_iteration.py:293-296).
 """
@@ -73,8 +74,8 @@ class RefModule:
         return fn
 
 
-def launch(fn, n_threads_total: int, args: list) -> None:
-    """fn<<<ceil(n/256), 256>>>(*args) on the legacy default stream."""
+def launch(fn, n_threads_total: int, args: list, blocks: int | None = None) -> None:
+    """fn<<<ceil(n/256), 256>>>(*args) on the legacy default stream (`blocks` overrides the grid)."""
     holders = []
     for a in args:
         if hasattr(a, "data_ptr"):
@@ -86,7 +87,8 @@ def launch(fn, n_threads_total: int, args: list) -> None:
         else:
             raise TypeError(type(a))
     arr = (C.c_void_p * len(holders))(*[C.addressof(h) for h in holders])
-    blocks = (n_threads_total + 255) // 256
+    if blocks is None:
+        blocks = (n_threads_total + 255) // 256
     _ck(_drv().cuLaunchKernel(fn, blocks, 1, 1, 256, 1, 1, 0, None, arr, None), "cuLaunchKernel")
 
 
@@ -150,6 +152,9 @@ class RefPolicyIteration:
         self.eval_kernel = self.module.get_function(meta["eval_kernel"])
         self.improve_kernel = self.module.get_function(meta["improve_kernel"])
         self.probe_kernel = self.module.get_function(meta["probe_kernel"])
+        self.mad_kernel = self.module.get_function(meta["max_abs_diff_kernel"]) if "max_abs_diff_kernel" in meta else None
+        self.d_delta = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._mad_blocks = min((self.n_states + 255) // 256, 8 * torch.cuda.get_device_properties(0).multi_processor_count)
         self.total_sweeps = 0
         self.pi_iterations = 0
 
@@ -167,7 +172,13 @@ class RefPolicyIteration:
             np.int32(self.n_states), np.int32(self.n_actions), np.float32(self.gamma)])
 
     def _max_abs_diff(self):
-        return (self.d_new_value_function - self.d_value_function).abs().max()
+        """max|new_V - V| as ONE fused pass (what cupy's ReductionKernel costs, :164-172)."""
+        if self.mad_kernel is None:
+            return (self.d_new_value_function - self.d_value_function).abs().max()
+        self.d_delta.zero_()
+        launch(self.mad_kernel, self.n_states, [self.d_new_value_function, self.d_value_function, np.int32(self.n_states),
+                                                self.d_delta], blocks=self._mad_blocks)
+        return self.d_delta
 
     # -- reference host loop (:300-370) ---------------------------------------
     def policy_evaluation(self) -> float:
@@ -207,19 +218,22 @@ class RefPolicyIteration:
         self.eval_launch()
         return self.d_new_value_function.cpu().numpy()
 
-    def probe_rows(self, a_idx: int):
+    def probe_rows(self, a_idx: int, s_begin: int = 0, count: int | None = None):
         """(idx, w, reward, terminated, next_state) produced by the reference's
-        step_dynamics + get_barycentric_Nd for action `a_idx` at every state."""
+        step_dynamics + get_barycentric_Nd for action `a_idx` at states [s_begin, s_begin + count)
+        (default: every state)."""
         torch = self.torch
         Cn = 1 << self.D
-        idx = torch.empty((self.n_states, Cn), dtype=torch.int32, device="cuda")
-        w = torch.empty((self.n_states, Cn), dtype=torch.float32, device="cuda")
-        r = torch.empty(self.n_states, dtype=torch.float32, device="cuda")
-        tm = torch.empty(self.n_states, dtype=torch.uint8, device="cuda")
-        nxt = torch.empty((self.n_states, self.D), dtype=torch.float32, device="cuda")
-        launch(self.probe_kernel, self.n_states, [
-            self.d_states, self.d_actions, np.int32(a_idx), self.d_bounds_low, self.d_bounds_high,
-            self.d_grid_shape, self.d_strides, np.int32(self.n_states), idx, w, r, tm, nxt])
+        n = self.n_states - s_begin if count is None else int(count)
+        states = self.d_states[s_begin:s_begin + n]
+        idx = torch.empty((n, Cn), dtype=torch.int32, device="cuda")
+        w = torch.empty((n, Cn), dtype=torch.float32, device="cuda")
+        r = torch.empty(n, dtype=torch.float32, device="cuda")
+        tm = torch.empty(n, dtype=torch.uint8, device="cuda")
+        nxt = torch.empty((n, self.D), dtype=torch.float32, device="cuda")
+        launch(self.probe_kernel, n, [
+            states, self.d_actions, np.int32(a_idx), self.d_bounds_low, self.d_bounds_high,
+            self.d_grid_shape, self.d_strides, np.int32(n), idx, w, r, tm, nxt])
         torch.cuda.synchronize()
         return idx.cpu().numpy(), w.cpu().numpy(), r.cpu().numpy(), tm.cpu().numpy(), nxt.cpu().numpy()
 

@@ -129,7 +129,10 @@ def test_host_device_handoff_and_device_handles():
     assert t.shape == (N,) and t.dtype == torch.float32
     # raw device handles are in the engine's storage order (pi_layout); host calls are in reference order
     np.testing.assert_array_equal(t.cpu().numpy(), eng.to_internal_order(V))
-    np.testing.assert_array_equal(eng.d_policy.get(), eng.to_internal_order(P))
+    np.testing.assert_array_equal(eng.d_policy.raw(), eng.to_internal_order(P))
+    # .get() is what a reference-style subclass calls on its cupy arrays: reference order, whatever the storage order
+    np.testing.assert_array_equal(eng.d_policy.get(), P)
+    np.testing.assert_array_equal(eng.d_value_function.get(), V)
     lay = eng.layout()
     assert sorted(lay["perm"]) == list(range(4)) and lay["perm"][-1] == lay["fast_dim"]
     eng.close()
