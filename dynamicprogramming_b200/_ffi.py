@@ -86,6 +86,7 @@ SIGNATURES = {
     "pi_set_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float]),
     "pi_set_values_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_float]),
     "pi_build_table": (C.c_int, [C.c_void_p]),
+    "pi_retrain": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_float, C.POINTER(C.c_int32)]),
     "pi_evaluate": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "pi_improve": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "pi_run": (C.c_int, [C.c_void_p, C.POINTER(PiStats)]),

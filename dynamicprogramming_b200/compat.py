@@ -20,6 +20,8 @@ override to store a goal value through a boolean mask (runners/overhead_crane_cu
   * `matplotlib.pyplot` -> ONLY when matplotlib is not importable: a stub whose functions raise a clear
     error when called, so `--no-plot` runs work and plotting fails loudly instead of silently.
 
+    python -m dynamicprogramming_b200.compat --serve      # one runner invocation per stdin line, engine kept (N4)
+
 The script's own `train()`, `evaluate()`, argparse block, `--bins` handling and `save()/load()` run as
 written; what changes is the class they subclass.  Nothing here touches oracle/.
 """
@@ -159,11 +161,49 @@ def run_runner(path: str | Path, argv: list[str]) -> None:
         sys.argv = old_argv
 
 
+def serve(stream=None) -> int:
+    """`--serve`: a long-lived trial loop.  Every line read from stdin is one runner invocation,
+    e.g. `runners/double_cartpole_swingup_cuda.py --bins 12 --episodes 3 --no-plot` — what runners/trial_runner.sh:38-44
+    passes to a fresh `python` per trial.  The script file is re-read for every line (so an edited dynamics / reward
+    string takes effect), but the process, the CUDA context and the native engine stay: the runner's `train()` builds
+    its object as always and the constructor takes over the parked engine of the previous trial (engine.keep_engines),
+    recompiling only the table builder when the dynamics text changed.  One `[serve] ...` status line per trial."""
+    import shlex
+    import time
+    import traceback
+
+    engine.keep_engines(True)
+    stream = sys.stdin if stream is None else stream
+    n = 0
+    for line in stream:
+        line = line.strip()
+        if not line or line.startswith("#"):
+            continue
+        if line in ("quit", "exit"):
+            break
+        argv = shlex.split(line)
+        t0 = time.perf_counter()
+        try:
+            run_runner(argv[0], argv[1:])
+            status = "ok"
+        except SystemExit as ex:      # argparse / sys.exit inside the runner must not end the server
+            status = f"exit {ex.code}"
+        except Exception:             # noqa: BLE001 - a broken trial is reported, the loop goes on
+            traceback.print_exc()
+            status = "error"
+        n += 1
+        print(f"[serve] trial {n} {status} in {time.perf_counter() - t0:.3f} s: {line}", flush=True)
+    engine.release_engines()
+    return 0
+
+
 def main(argv: list[str] | None = None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv or argv[0] in ("-h", "--help"):
         print(__doc__)
         return 0 if argv else 2
+    if argv[0] == "--serve":
+        return serve()
     run_runner(argv[0], argv[1:])
     return 0
 

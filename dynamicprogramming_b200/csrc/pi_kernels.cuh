@@ -1025,6 +1025,36 @@ __global__ void __launch_bounds__(1024) eval_reduce_kernel(Ctl* ctl, const float
     }
 }
 
+// First level of a two-level reduction of the per-block partials (max of floats / sum of counts): the one-block
+// final kernels above read 500 000 partials of a 64 M-state sweep in 204 us; 256 blocks bring that to a few us.
+__global__ void __launch_bounds__(256) partial_max_kernel(const float* __restrict__ in, int n, float* __restrict__ out) {
+    float r = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) r = fmaxf(r, in[i]);
+    __shared__ float s_red[8];
+    r = warp_max(r);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < 8 ? s_red[threadIdx.x] : 0.0f;
+        r = warp_max(r);
+        if (threadIdx.x == 0) out[blockIdx.x] = r;
+    }
+}
+__global__ void __launch_bounds__(256) partial_sum_kernel(const unsigned* __restrict__ in, int n, unsigned* __restrict__ out) {
+    unsigned r = 0;   // a block sums at most n / gridDim counts of <= 256 each: no overflow below 2^24 partials per block
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) r += in[i];
+    __shared__ unsigned s_red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < 8; ++i) t += s_red[i];
+        out[blockIdx.x] = t;
+    }
+}
+
 __global__ void eval_decide_kernel(Ctl* ctl, const float* delta_src, float theta) {
     if (ctl->done) return;
     const float d = *delta_src;

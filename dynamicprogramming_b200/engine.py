@@ -52,10 +52,35 @@ class CudaPIConfig:
     log_interval: int = 100
 
 
+# ── N4: engines kept alive across trainings ──────────────────────────────────────────────────────────────────────
+# The autoresearch loop of the reference (runners/trial_runner.sh:33-60) trains the same grid again and again with an
+# edited dynamics / reward string.  With keep_engines(True) (or DPB200_KEEP_ENGINE=1) `close()` parks the native engine
+# instead of destroying it, and the next constructor call for the SAME grid, action set, config, device and shard takes
+# it over through pi_retrain: CUDA context, buffers, storage order, JIT sweep kernels, graphs and communicator are
+# reused; only the table builder is recompiled (when the text changed) and the table rebuilt.
+_KEEP_ENGINES = os.environ.get("DPB200_KEEP_ENGINE", "0") not in ("0", "", "off")
+_ENGINE_POOL: dict = {}
+
+
+def keep_engines(on: bool = True) -> None:
+    """Enable / disable parking of native engines on close() (see above); disabling releases the parked ones."""
+    global _KEEP_ENGINES
+    _KEEP_ENGINES = bool(on)
+    if not on:
+        release_engines()
+
+
+def release_engines() -> None:
+    """Destroy every parked engine (frees its VRAM)."""
+    while _ENGINE_POOL:
+        _, handle = _ENGINE_POOL.popitem()
+        _ffi.lib().pi_destroy(handle)
+
+
 # states above which `_terminal_fn` is evaluated slab by slab instead of on the
 # fully materialised (N, D) array (host memory / time; results are identical
 # for the element-wise masks every reference environment uses).
-_CHUNK_STATES = int(os.environ.get("DPB200_TERMINAL_CHUNK", 16_000_000))
+_CHUNK_STATES = int(os.environ.get("DPB200_TERMINAL_CHUNK", 2_000_000))
 
 
 class DeviceArray:
@@ -239,10 +264,17 @@ class _CudaPolicyIterationBase(abc.ABC):
             sh.rank, sh.world_size = int(self._shard[0]), int(self._shard[1])
             C.memmove(sh.nccl_id, bytes(self._shard[2]), 128)
             shard_p = C.byref(sh)
-        handle = C.c_void_p()
-        _ffi.check(lib.pi_create(C.byref(grid), self.action_space.ctypes.data_as(C.POINTER(C.c_float)),
-                                 self.n_actions, C.byref(cfg), self._dynamics_cuda_src().encode(), self._device,
-                                 shard_p, C.byref(handle)))
+        self._pool_key = None
+        if self._shard is None or self._shard[1] <= 1:
+            self._pool_key = (D, tuple(a.tobytes() for a in self._axes), self.action_space.tobytes(),
+                              (cfg.gamma, cfg.theta, cfg.max_eval_iter, cfg.max_pi_iter, cfg.log_interval), self._device)
+        handle = _ENGINE_POOL.pop(self._pool_key, None) if _KEEP_ENGINES and self._pool_key is not None else None
+        reused = handle is not None
+        if not reused:
+            handle = C.c_void_p()
+            _ffi.check(lib.pi_create(C.byref(grid), self.action_space.ctypes.data_as(C.POINTER(C.c_float)),
+                                     self.n_actions, C.byref(cfg), self._dynamics_cuda_src().encode(), self._device,
+                                     shard_p, C.byref(handle)))
         self._engine = handle
 
         levels = {0: logger.debug, 1: logger.info, 2: logger.success, 3: logger.warning}
@@ -251,11 +283,36 @@ class _CudaPolicyIterationBase(abc.ABC):
 
         terminal_mask, terminal_value = self._terminal_mask_and_value()
         self._terminal_mask_host = np.ascontiguousarray(terminal_mask, dtype=np.uint8)
-        if self._terminal_mask_host.any():
+        has_terminal = bool(self._terminal_mask_host.any())
+        if reused:
+            self._retrain_native(has_terminal, terminal_value)
+        elif has_terminal:
             _ffi.check(lib.pi_set_terminal(self._engine, _ffi.ptr(self._terminal_mask_host), float(terminal_value)))
+        if has_terminal:
             logger.info(f"Terminal states: {int(terminal_mask.sum()):,} (value={terminal_value})")
         self._refresh_device_handles()
         logger.success("CUDA kernels compiled. VRAM allocated.")
+
+    def _retrain_native(self, has_terminal: bool, terminal_value: float) -> bool:
+        """pi_retrain with this object's current dynamics text and terminal mask; True if the builder was recompiled."""
+        recompiled = C.c_int32()
+        mask = _ffi.ptr(self._terminal_mask_host) if has_terminal else None
+        _ffi.check(_ffi.lib().pi_retrain(self._engine, self._dynamics_cuda_src().encode(), mask, float(terminal_value),
+                                         C.byref(recompiled)))
+        self._table_ready = True
+        return bool(recompiled.value)
+
+    def retrain(self) -> bool:
+        """In-process counterpart of a new trial: re-read `_dynamics_cuda_src()` / `_terminal_fn` from this object (a
+        subclass instance whose reward or dynamics parameters were edited), rebuild the transition table and reset V
+        and the policy — keeping the CUDA context, buffers, JIT sweep kernels, graphs and communicator
+        (include/dpb200.h: pi_retrain).  Returns True if the dynamics text changed and was recompiled.  Follow with
+        policy_evaluation() / policy_improvement() or run()."""
+        terminal_mask, terminal_value = self._terminal_mask_and_value()
+        self._terminal_mask_host = np.ascontiguousarray(terminal_mask, dtype=np.uint8)
+        out = self._retrain_native(bool(self._terminal_mask_host.any()), terminal_value)
+        self._refresh_device_handles()
+        return out
 
     def _refresh_device_handles(self) -> None:
         lib = _ffi.lib()
@@ -336,7 +393,12 @@ class _CudaPolicyIterationBase(abc.ABC):
 
     def close(self) -> None:
         if getattr(self, "_engine", None):
-            _ffi.lib().pi_destroy(self._engine)
+            key = getattr(self, "_pool_key", None)
+            if _KEEP_ENGINES and key is not None and key not in _ENGINE_POOL and len(_ENGINE_POOL) < 2:
+                _ffi.lib().pi_set_log(self._engine, _ffi.LOG_FN(0), None)   # the callback dies with this object
+                _ENGINE_POOL[key] = self._engine                           # parked: the next constructor for this grid retrains it
+            else:
+                _ffi.lib().pi_destroy(self._engine)
             self._engine = None
             for attr in ("d_value_function", "d_new_value_function", "d_policy", "d_terminal_mask"):
                 if hasattr(self, attr):

@@ -144,6 +144,15 @@ int pi_set_values_buffer(pi_engine* e, int32_t which, const uint8_t* mask, float
  * n_dims interpolation fractions, reward.  Must follow pi_set_terminal. */
 int pi_build_table(pi_engine* e);
 
+/* N4 — a persistent engine across autoresearch trials (runners/trial_runner.sh:33-60 starts a new Python process per trial;
+ * only the dynamics / reward text of runners/double_cartpole_swingup_cuda.py changes between trials).  pi_retrain puts
+ * the engine back into its freshly constructed state — V := 0, policy := 0, the given terminal mask / value (NULL: none) —
+ * and rebuilds the transition table, recompiling the builder only when `dynamics_src` differs from the text it was built
+ * from (*recompiled).  Everything that does not depend on the dynamics is kept: CUDA context, buffers, storage order,
+ * the JIT-compiled sweep kernels, CUDA graphs, the NCCL communicator and the peer mappings.  Equivalent to
+ * pi_destroy + pi_create + pi_set_terminal + pi_build_table for the same grid, bit for bit. */
+int pi_retrain(pi_engine* e, const char* dynamics_src, const uint8_t* terminal_mask, float terminal_value, int32_t* recompiled);
+
 /* policy_evaluation() (src/cuda_policy_iteration.py:300-336): Jacobi sweeps,
  * residual read every sync_interval sweeps, returns at the first sync sweep
  * with delta < theta.  *delta = value the reference would return; *sweeps =

@@ -30,13 +30,18 @@ XL4 = {"DPB200_FAST_DIM": "0", "DPB200_XLINE": "force:4,0,4,8,1,1:1,6,12"}
 # the JIT generic sweeps (one state per thread with grouped gathers — the default of large 6-D grids — and packed pairs)
 GP1 = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:128,8,2,8,1"}
 GP2 = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:64,8,2,8,0"}
+# the plane-staged sweep (TMA-staged V-planes; needs plane-aligned shard boundaries), default and with few slots / ragged chunks
+PL = {"DPB200_PLANE": "force"}
+PL2 = {"DPB200_PLANE": "force:40,7,2,2,1"}
 cases = [("cartpole", 12, 4, {}), ("mountain_car", 60, None, {}), ("double_pendulum_swingup", 10, 3, {}),
          ("double_cartpole_swingup", 7, 2, {}), ("pendulum", 33, 6, {}),
          ("double_cartpole_swingup", 8, 2, XL), ("cartpole_swingup", 12, 3, XL4),
-         ("double_cartpole_swingup", 7, 2, GP1), ("cartpole_swingup", 11, 3, GP1), ("double_cartpole", 6, 2, GP2)]
+         ("double_cartpole_swingup", 7, 2, GP1), ("cartpole_swingup", 11, 3, GP1), ("double_cartpole", 6, 2, GP2),
+         ("double_cartpole_swingup", 8, 3, PL), ("cartpole", 12, 4, PL), ("double_cartpole", 6, 2, PL2),
+         ("double_cartpole_swingup", 10, 2, PL2)]
 ok = True
 for env, bins, max_pi, engine_env in cases:
-    for k in ("DPB200_FAST_DIM", "DPB200_XLINE", "DPB200_PAIR"):
+    for k in ("DPB200_FAST_DIM", "DPB200_XLINE", "DPB200_PAIR", "DPB200_PLANE"):
         os.environ.pop(k, None)
     os.environ.update(engine_env)
     spec = envs.REGISTRY[env]
@@ -47,7 +52,9 @@ for env, bins, max_pi, engine_env in cases:
     eng = spec.make(bins=bins, config=cfg, device=local, shard=shard)
     eng.build_table()
     kernel = eng.eval_kernel_info()["kernel"]
-    if "DPB200_PAIR" in engine_env:
+    if "DPB200_PLANE" in engine_env:
+        assert "ps_sweep" in kernel, kernel
+    elif "DPB200_PAIR" in engine_env:
         assert "gp_sweep" in kernel, kernel
     elif engine_env:
         assert "xl_sweep" in kernel, kernel
@@ -56,6 +63,7 @@ for env, bins, max_pi, engine_env in cases:
     if rank == 0:
         os.environ["DPB200_XLINE"] = "off"
         os.environ["DPB200_PAIR"] = "off"
+        os.environ["DPB200_PLANE"] = "off"
         one = spec.make(bins=bins, config=cfg, device=local)
         one.run()
         res.update(pi_1gpu=one.pi_iterations, sweeps_1gpu=one.total_eval_sweeps,
