@@ -106,6 +106,9 @@ __device__ __forceinline__ void store_peers(const PeerOut& po, bool out_is_V0, l
 // Cross-GPU barrier at the end of a sweep: thread t publishes this rank's epoch into rank t's flag
 // array (release, system scope — the sweep kernel before it in stream order has completed, so its
 // peer stores are performed), then waits until rank t's epoch has arrived in the local array.
+// Only ranks that exchange values take part (`partners`): with contiguous ranges of the slowest-stored
+// dimension that is the two neighbours (plus the wrap-around partner of a periodic angle), not all 7
+// peers, so a sweep waits for the slowest of 3 ranks instead of the slowest of 8.
 // flags_local[r] is written only by rank r.  A rank that never arrives (crashed peer) trips the
 // timeout instead of hanging the GPU; the host turns err != 0 into PI_ERR_COMM.
 struct BarrierParams {
@@ -117,12 +120,14 @@ struct BarrierParams {
     long long timeout_ticks;               // clock64 ticks a rank waits for a peer (DPB200_BARRIER_TIMEOUT_S, default 120 s)
     int rank;
     int world;
+    unsigned partners;                     // bit r: rank r exchanges values with this rank (either direction); only those
+                                           // pairs synchronise — the relation is symmetric, both sides compute it from the plan
 };
 __global__ void xgpu_barrier_kernel(const BarrierParams b) {
     const int t = threadIdx.x;
     const unsigned e = *b.epoch + 1;
     if (*b.err) return;   // a barrier already timed out in this call: do not wait again, the host reports PI_ERR_COMM
-    if (t < b.world && t != b.rank) {
+    if (t < b.world && t != b.rank && ((b.partners >> t) & 1u)) {
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(b.flags_peer[t] + b.rank), "r"(e) : "memory");
         const long long t0 = clock64();

@@ -54,6 +54,7 @@ __device__ __forceinline__ void ps_store_peers(const PsPeerOut& po, bool out_is_
 #define PS_MAXOC 16        // outer corners per cell (2^(D-2), D <= 6)
 #define PS_MAXLOADS 80     // plane loads per step
 #define PS_FALLBACK 0x40000000
+#define PS_BAD_SLOT (0xffffu << 4)   // staged slot offset of a cell that is not resident (pi::kPlanBadSlot << 4)
 
 struct PsRec {   // == pi::PlaneRec (plane_plan.cuh)
     unsigned char n_early, n_late, n_cells, flags;
@@ -362,7 +363,9 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
                 ps_mbar_wait(&full[b], (it >> 1) & 1);
 
                 float ev = 0.0f;
-                if (staged) {
+                // a cell whose V-planes found no slot is marked in its slot offsets (plane_slots_kernel): gather from global
+                const bool resident = staged && cs_s[b * PS_CS_WORDS + k * PS_MAXOC] != PS_BAD_SLOT;
+                if (resident) {
                     const unsigned* csk = cs_s + b * PS_CS_WORDS + k * PS_MAXOC;
                     const unsigned char* sbase = ps_smem + ip * 4u;
 #if PS_PACK
