@@ -52,9 +52,11 @@ struct GpPeerOut {
     long long lo[7];
     long long hi[7];
 };
+// unrolled over the 7 entries: a run-time-indexed loop over a kernel-parameter struct is compiled into local-memory copies
 __device__ __forceinline__ void gp_store_peers(const GpPeerOut& po, bool out_is_V0, long long g, float v) {
-    for (int r = 0; r < po.n; ++r)
-        if (g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
+#pragma unroll
+    for (int r = 0; r < 7; ++r)
+        if (r < po.n && g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
 }
 
 struct GpParams {
@@ -70,6 +72,10 @@ struct GpParams {
     int j;
     int check;
     GpPeerOut peers;
+    int rot;                     // sharded runs: block visited first (blocks whose values peers need go first); 0 on one GPU
+    int n_peer_blocks;           // ... and how many blocks from there on can hold states a peer needs (the rest is interior)
+    int sched_begin;             // one state per thread: this launch sweeps blocks [sched_begin, sched_begin + gridDim.x) of the (rotated)
+    int n_blocks;                // schedule of n_blocks blocks (sharded runs with the DMA exchange launch boundary and interior separately)
     float2* P0;                  // GP_PAIRV: pair shadow of V0, P0[i] = (V0[i], V0[i+1]); else unused
     float2* P1;                  //           ... of V1
 };
@@ -188,7 +194,11 @@ extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const
     const float* __restrict__ Vin = par ? p.V1 : p.V0;
     float* __restrict__ Vout = par ? p.V0 : p.V1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long s = (long long)blockIdx.x * GP_THREADS + threadIdx.x;
+    const unsigned sched = blockIdx.x + (unsigned)p.sched_begin;
+    const unsigned blk = sched + (unsigned)p.rot < (unsigned)p.n_blocks ? sched + (unsigned)p.rot : sched + (unsigned)p.rot - (unsigned)p.n_blocks;
+    const long long s = (long long)blk * GP_THREADS + threadIdx.x;
+    // peers need values only from the first blocks of the (rotated) schedule
+    const bool peer_blk = sched < (unsigned)p.n_peer_blocks;
 #if GP_PAIRV
     const float2* __restrict__ Pin = par ? p.P1 : p.P0;
     float2* __restrict__ Pout = par ? p.P0 : p.P1;
@@ -288,7 +298,7 @@ extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const
             if (g > 0) Pout[g - 1].y = vnew;
         }
 #endif
-        if (p.peers.n) gp_store_peers(p.peers, par != 0, p.s_begin + s, vnew);
+        if (peer_blk) gp_store_peers(p.peers, par != 0, p.s_begin + s, vnew);
         res = fabsf(vnew - vold);
     }
     if (!p.check) return;
@@ -299,7 +309,7 @@ extern "C" __global__ void __launch_bounds__(GP_THREADS, GP_MINB) gp_sweep(const
     if (threadIdx.x < 32) {
         float r = threadIdx.x < GP_THREADS / 32 ? s_red[threadIdx.x] : 0.0f;
         r = gp_warp_max(r);
-        if (threadIdx.x == 0) p.partial[blockIdx.x] = r;
+        if (threadIdx.x == 0) p.partial[sched] = r;
     }
 }
 #else

@@ -45,9 +45,11 @@ struct PsPeerOut {   // == pi::PeerOut
     long long lo[7];
     long long hi[7];
 };
+// unrolled over the 7 entries: a run-time-indexed loop over a kernel-parameter struct is compiled into local-memory copies
 __device__ __forceinline__ void ps_store_peers(const PsPeerOut& po, bool out_is_V0, long long g, float v) {
-    for (int r = 0; r < po.n; ++r)
-        if (g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
+#pragma unroll
+    for (int r = 0; r < 7; ++r)
+        if (r < po.n && g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
 }
 
 #define PS_MAXC 8          // staged successor cells per state-plane
@@ -76,6 +78,12 @@ struct PsParams {
     long long s_begin;
     int n_planes;                // local state-planes
     int n_chunks;
+    int chunk_rot;               // sharded runs: chunk visited first (the chunks whose values peers need go first, so their NVLink
+                                 // stores drain while the interior is swept); 0 on one GPU
+    int n_peer_chunks;           // ... and how many chunks from there on can hold states a peer needs (the rest is interior)
+    int sched_begin;             // this launch sweeps the chunks [sched_begin, sched_end) of the (rotated) schedule: sharded runs with
+    int sched_end;               // the DMA exchange launch the boundary part and the interior part separately
+    int partial_off;             // first slot of p.partial this launch writes
     float gamma;
     int j;
     int check;
@@ -294,7 +302,8 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
             return *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(r->cs) + lane * 4);
         };
         bool armed = false;   // full[it & 1] was already armed one step ahead
-        for (int chunk = blockIdx.x; chunk < p.n_chunks; chunk += gridDim.x) {
+        for (int ci = p.sched_begin + blockIdx.x; ci < p.sched_end; ci += gridDim.x) {
+            const int chunk = ci + p.chunk_rot < p.n_chunks ? ci + p.chunk_rot : ci + p.chunk_rot - p.n_chunks;
             const int pl0 = chunk * PS_L;
             const int Lc = (p.n_planes - pl0) < PS_L ? (p.n_planes - pl0) : PS_L;
             const PsRec* rec = p.plan + pl0;
@@ -358,9 +367,13 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
         }
     } else {
         // ------------------------------------------------------------------ consumer warps
-        for (int chunk = blockIdx.x; chunk < p.n_chunks; chunk += gridDim.x) {
+        for (int ci = p.sched_begin + blockIdx.x; ci < p.sched_end; ci += gridDim.x) {
+            const int chunk = ci + p.chunk_rot < p.n_chunks ? ci + p.chunk_rot : ci + p.chunk_rot - p.n_chunks;
             const int pl0 = chunk * PS_L;
             const int Lc = (p.n_planes - pl0) < PS_L ? (p.n_planes - pl0) : PS_L;
+            // peers need values only from the first chunks of the (rotated) schedule: the per-state range tests and stores
+            // run only there
+            const bool peer_plane = ci < p.n_peer_chunks;
             unsigned w[PS_W];
             if (has_state) ps_load_row(p, (long long)pl0 * PS_P + tid, w);
             for (int i = 0; i < Lc; ++i, ++it) {
@@ -472,7 +485,7 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
                 if (has_state) {
                     const float vnew = code == -2 ? vold : fmaf(p.gamma, ev, reward);
                     Vout[g] = vnew;
-                    if (p.peers.n) ps_store_peers(p.peers, par != 0, g, vnew);
+                    if (peer_plane) ps_store_peers(p.peers, par != 0, g, vnew);
                     if (p.check) res = fmaxf(res, fabsf(vnew - vold));
                 }
                 __syncwarp();
@@ -488,6 +501,6 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
     if (tid < 32) {
         float r = tid < (PS_THREADS + 32) / 32 ? s_red[tid] : 0.0f;
         r = ps_warp_max(r);
-        if (tid == 0) p.partial[blockIdx.x] = r;
+        if (tid == 0) p.partial[p.partial_off + blockIdx.x] = r;
     }
 }

@@ -52,9 +52,11 @@ struct XlPeerOut {
     long long lo[7];
     long long hi[7];
 };
+// unrolled over the 7 entries: a run-time-indexed loop over a kernel-parameter struct is compiled into local-memory copies
 __device__ __forceinline__ void xl_store_peers(const XlPeerOut& po, bool out_is_V0, long long g, float v) {
-    for (int r = 0; r < po.n; ++r)
-        if (g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
+#pragma unroll
+    for (int r = 0; r < 7; ++r)
+        if (r < po.n && g >= po.lo[r] && g < po.hi[r]) (out_is_V0 ? po.V0[r] : po.V1[r])[g] = v;
 }
 
 struct XlParams {

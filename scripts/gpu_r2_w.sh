@@ -1,0 +1,5 @@
+#!/bin/bash
+( timeout 600 python scripts/exp_plane.py 20 "0,20,2,2,0" "0,10,2,2,0" "0,5,2,2,0" "0,4,2,2,0" ) > gpurun_out/r2w_exp_plane.log 2>&1; grep ms_plane gpurun_out/r2w_exp_plane.log | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['cfg'], round(d['ms_plane'],4), round(d['ms_base'],4), round(d['loads_per_plane'],1), round(d['late_per_plane'],1), d['grid'])"
