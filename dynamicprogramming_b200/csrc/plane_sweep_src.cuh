@@ -110,6 +110,7 @@ struct PsParams {
 #endif
 #define PS_SLOTS_BYTES (PS_NS * PS_PITCH)
 #define PS_CS_WORDS (PS_MAXC * PS_MAXOC)
+#define PS_NOUT 4                    // output planes in flight (ring): written by the consumers of step it, stored by TMA after it
 
 // ------------------------------------------------------------------ mbarrier / TMA bulk copy
 __device__ __forceinline__ unsigned ps_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -146,6 +147,16 @@ __device__ __forceinline__ void ps_bulk_load(void* dst, const void* src, unsigne
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(ps_saddr(dst)), "l"(src), "r"(bytes), "r"(ps_saddr(b)) : "memory");
 }
+
+// one contiguous plane of new values: shared -> global (local V buffer or a peer's, over NVLink), bulk async-group completion
+__device__ __forceinline__ void ps_bulk_store(void* dst, const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ps_saddr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ps_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ps_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ps_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ps_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ float ps_warp_max(float v) {
 #pragma unroll
@@ -254,6 +265,7 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
     unsigned* const cs_s = reinterpret_cast<unsigned*>(ps_smem + PS_SLOTS_BYTES);                    // [2][PS_CS_WORDS] slot byte offsets
     ps_u64* const full = reinterpret_cast<ps_u64*>(ps_smem + PS_SLOTS_BYTES + 2 * PS_CS_WORDS * 4);   // [2]
     ps_u64* const done = full + 2;                                                                   // [2]
+    float* const out_s = reinterpret_cast<float*>(ps_smem + PS_SLOTS_BYTES + 2 * PS_CS_WORDS * 4 + 32);   // [PS_NOUT][PS_P] new values of a plane
     __shared__ float s_red[(PS_THREADS + 32) / 32];
 
     const PsCtl* __restrict__ ctl = p.ctl;
@@ -301,6 +313,23 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
         auto fetch_cs = [&](const PsRec* r) {
             return *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(r->cs) + lane * 4);
         };
+        // The new values of a plane leave through shared memory too: the consumers write them into out_s[it % PS_NOUT], and once
+        // every consumer warp is done with the step this warp stores the whole plane with ONE TMA bulk copy into the local V
+        // buffer — and with one more per peer that needs the plane (sharded runs: peer buffers over NVLink; the ranges peers
+        // need are rounded to whole planes by the host).  No store instruction of the backup threads touches global memory.
+        long long prev_g0 = -1;   // first global state of the plane of the previous step
+        auto store_plane = [&](unsigned step, long long g0) {
+            if (lane == 0) {
+                const float* src = out_s + (size_t)(step % PS_NOUT) * PS_P;
+                ps_bulk_store(Vout + g0, src, PS_PLANE_BYTES);
+                for (int r = 0; r < p.peers.n; ++r)
+                    if (g0 >= p.peers.lo[r] && g0 + PS_P <= p.peers.hi[r])
+                        ps_bulk_store((par ? p.peers.V0[r] : p.peers.V1[r]) + g0, src, PS_PLANE_BYTES);
+                ps_bulk_commit();
+                ps_bulk_wait_read<PS_NOUT - 2>();   // the buffer the consumers may write next (step + 2) has been read out
+            }
+            __syncwarp();
+        };
         bool armed = false;   // full[it & 1] was already armed one step ahead
         for (int ci = p.sched_begin + blockIdx.x; ci < p.sched_end; ci += gridDim.x) {
             const int chunk = ci + p.chunk_rot < p.n_chunks ? ci + p.chunk_rot : ci + p.chunk_rot - p.n_chunks;
@@ -337,6 +366,8 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
 #endif
                 // every consumer warp is done with the previous step: its slots (and the other cs buffer) are free
                 if (it > 0) ps_mbar_wait(&done[b ^ 1], ((it - 1) >> 1) & 1);
+                if (prev_g0 >= 0) store_plane(it - 1, prev_g0);
+                prev_g0 = p.s_begin + (long long)(pl0 + i) * PS_P;
                 if (!armed) {
                     stage_cs_regs(cs_cur, b);
                     __syncwarp();
@@ -365,15 +396,17 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
                 }
             }
         }
+        if (prev_g0 >= 0) {   // the last plane of this CTA
+            ps_mbar_wait(&done[(it - 1) & 1], ((it - 1) >> 1) & 1);
+            store_plane(it - 1, prev_g0);
+        }
+        if (lane == 0) ps_bulk_wait_all();   // every plane of new values has landed before the kernel ends
     } else {
         // ------------------------------------------------------------------ consumer warps
         for (int ci = p.sched_begin + blockIdx.x; ci < p.sched_end; ci += gridDim.x) {
             const int chunk = ci + p.chunk_rot < p.n_chunks ? ci + p.chunk_rot : ci + p.chunk_rot - p.n_chunks;
             const int pl0 = chunk * PS_L;
             const int Lc = (p.n_planes - pl0) < PS_L ? (p.n_planes - pl0) : PS_L;
-            // peers need values only from the first chunks of the (rotated) schedule: the per-state range tests and stores
-            // run only there
-            const bool peer_plane = ci < p.n_peer_chunks;
             unsigned w[PS_W];
             if (has_state) ps_load_row(p, (long long)pl0 * PS_P + tid, w);
             for (int i = 0; i < Lc; ++i, ++it) {
@@ -484,10 +517,10 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
                 }
                 if (has_state) {
                     const float vnew = code == -2 ? vold : fmaf(p.gamma, ev, reward);
-                    Vout[g] = vnew;
-                    if (peer_plane) ps_store_peers(p.peers, par != 0, g, vnew);
+                    out_s[(it % PS_NOUT) * PS_P + tid] = vnew;
                     if (p.check) res = fmaxf(res, fabsf(vnew - vold));
                 }
+                ps_fence_async_smem();   // the plane is read by the TMA store (async proxy)
                 __syncwarp();
                 if (lane == 0) ps_mbar_arrive(&done[b]);
             }
