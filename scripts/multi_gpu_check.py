@@ -33,15 +33,16 @@ GP2 = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:64,8,2,8,0"}
 # the plane-staged sweep (TMA-staged V-planes; needs plane-aligned shard boundaries), default and with few slots / ragged chunks
 PL = {"DPB200_PLANE": "force"}
 PL2 = {"DPB200_PLANE": "force:40,7,2,2,1"}
-# the same sweeps with the in-kernel peer stores instead of the default DMA exchange (boundary part, copy engines, interior part)
-PLp = {"DPB200_PLANE": "force", "DPB200_EXCHANGE": "p2p"}
-GP1p = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:128,8,2,8,1", "DPB200_EXCHANGE": "p2p"}
+# the gather sweep with the opt-in DMA exchange (boundary part, copy engines, interior part) instead of in-kernel peer stores,
+# and both JIT sweeps over NCCL send/recv
+GP1d = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:128,8,2,8,1", "DPB200_EXCHANGE": "dma"}
+PLn = {"DPB200_PLANE": "force", "DPB200_EXCHANGE": "nccl"}
 cases = [("cartpole", 12, 4, {}), ("mountain_car", 60, None, {}), ("double_pendulum_swingup", 10, 3, {}),
          ("double_cartpole_swingup", 7, 2, {}), ("pendulum", 33, 6, {}),
          ("double_cartpole_swingup", 8, 2, XL), ("cartpole_swingup", 12, 3, XL4),
          ("double_cartpole_swingup", 7, 2, GP1), ("cartpole_swingup", 11, 3, GP1), ("double_cartpole", 6, 2, GP2),
          ("double_cartpole_swingup", 8, 3, PL), ("cartpole", 12, 4, PL), ("double_cartpole", 6, 2, PL2),
-         ("double_cartpole_swingup", 10, 2, PL2), ("double_cartpole_swingup", 8, 3, PLp), ("double_cartpole_swingup", 7, 2, GP1p)]
+         ("double_cartpole_swingup", 10, 2, PL2), ("double_cartpole_swingup", 8, 3, PLn), ("double_cartpole_swingup", 7, 2, GP1d)]
 ok = True
 for env, bins, max_pi, engine_env in cases:
     for k in ("DPB200_FAST_DIM", "DPB200_XLINE", "DPB200_PAIR", "DPB200_PLANE", "DPB200_EXCHANGE"):

@@ -90,14 +90,19 @@ def test_k5_transition_rows_match_the_reference_slab_wise(ref_runner):
     eng.build_table()
     ref = ref_runner.from_engine_env(env, bins=bins)
     n = 160_000
-    for a, s0 in ((0, 0), (4, 13_333_337), (8, 31_999_999), (2, 50_000_000), (6, 64_000_000 - n)):
+    compared = 0
+    for a, s0 in ((0, 0), (1, 3_200_000), (4, 13_333_337), (8, 31_999_999), (2, 50_000_000), (6, 60_500_000),
+                  (7, 64_000_000 - n)):
         idx, w, r, t = eng.expand_rows(a, s0, n)
         ridx, rw, rr, rt, _ = ref.probe_rows(a, s0, n)
-        live = rt == 0
-        np.testing.assert_array_equal(t != 0, rt != 0)
+        own = t != 2                      # states in the terminal mask have no row (new_V := V, :1053); the probe ignores the mask
+        live = own & (rt == 0)
+        np.testing.assert_array_equal((t == 1)[own], (rt != 0)[own])
         np.testing.assert_array_equal(idx[live], ridx[live])
         np.testing.assert_array_equal(bits(w[live]), bits(rw[live]))
-        np.testing.assert_array_equal(bits(r), bits(rr))
+        np.testing.assert_array_equal(bits(r[own]), bits(rr[own]))
+        compared += int(own.sum())
+    assert compared >= 4 * n          # the first and the last slab (and the end of the sixth) lie in the terminal mask |x| > 2.4
     eng.close()
 
 
