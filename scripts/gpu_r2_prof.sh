@@ -1,5 +1,5 @@
 #!/bin/bash
+# ncu --set full of the plane-staged K5 sweep under the bench policy (the 70th ps_sweep launch of scripts/prof_plane.py:
+# 4 autotune probes + 50 sweeps of policy 0 come first) -> profiles/r02_ncu_summary_ps_sweep.txt
 mkdir -p gpurun_out
-( time timeout 600 python -m pytest tests/test_gpu_fullsize_parity.py -x -q -k "slab" ) > gpurun_out/r2_par.log 2>&1; grep -E "passed|failed" gpurun_out/r2_par.log
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"pi_build_rows|improve_kernel|compact_rows_kernel|plane_cells_kernel|plane_slots_kernel" -s 144 -c 8 --csv --log-file gpurun_out/r02_k5_kernels.csv python scripts/prof_plane.py 20 > /dev/null 2>&1
-grep -c . gpurun_out/r02_k5_kernels.csv
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-id ::ps_sweep:70 -o gpurun_out/r02_ps_sweep python scripts/prof_plane.py 20 > gpurun_out/r02_prof.log 2>&1; tail -2 gpurun_out/r02_prof.log

@@ -16,5 +16,5 @@ if len(sys.argv) <= 3:
     eng.sweeps(50)
     eng.policy_improvement()
 print(eng.eval_kernel_info())
-d, ms = eng.sweeps(5)
-print("ms/sweep", ms / 5)
+d, ms = eng.sweeps(25)
+print("ms/sweep", ms / 25)
