@@ -81,6 +81,9 @@ def release_engines() -> None:
 # fully materialised (N, D) array (host memory / time; results are identical
 # for the element-wise masks every reference environment uses).
 _CHUNK_STATES = int(os.environ.get("DPB200_TERMINAL_CHUNK", 2_000_000))
+# ... unless the plugin stashes per-state arrays inside `_terminal_fn`: up to this size it then gets the whole grid in one
+# call (the reference's behaviour); above it the stashed slabs are stitched (host memory: N x D x 4 bytes)
+_FULL_STATES_MAX = 16_000_000
 
 
 class DeviceArray:
@@ -240,6 +243,11 @@ class _CudaPolicyIterationBase(abc.ABC):
             for k, v in vars(self).items():
                 if isinstance(v, np.ndarray) and v.shape[:1] == (inner,) and before.get(k) != id(v):
                     stashed.setdefault(k, []).append(v.copy())
+            if i == 0 and stashed and self.n_states <= _FULL_STATES_MAX:
+                # the plugin keeps per-state arrays from _terminal_fn (the crane's goal mask): give it the whole grid at once,
+                # exactly as the reference does, instead of stitching slabs back together
+                mask, value = self._terminal_fn(self.states_space)
+                return np.asarray(mask, dtype=bool), float(value)
         for k, parts in stashed.items():
             if len(parts) == len(self._axes[0]):
                 setattr(self, k, np.concatenate(parts))
