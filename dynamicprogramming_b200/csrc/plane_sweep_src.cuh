@@ -110,7 +110,9 @@ struct PsParams {
 #endif
 #define PS_SLOTS_BYTES (PS_NS * PS_PITCH)
 #define PS_CS_WORDS (PS_MAXC * PS_MAXOC)
+#ifndef PS_NOUT
 #define PS_NOUT 4                    // output planes in flight (ring): written by the consumers of step it, stored by TMA after it
+#endif
 
 // ------------------------------------------------------------------ mbarrier / TMA bulk copy
 __device__ __forceinline__ unsigned ps_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
