@@ -65,6 +65,13 @@ struct PlanParams {
     int noc;                     // outer corners per cell (power of two)
     int pitch;                   // floats between slots in shared memory (>= P, multiple of 4)
     int ooff[kPlanMaxOC];        // V-plane offset of outer corner j
+    // item mode (plane_items_kernel): the states of a plane regrouped into P/2 work items of two states each
+    unsigned char* irows;        // out: [plane][quarter q < nq][item slot < T] of 16 bytes
+    long long n_pad;             // states per row plane of `rows`
+    int W;                       // words per row (D + 2)
+    int nq;                      // 16-byte quarters per item: ceil(2 W / 4)
+    int T;                       // item slots per state-plane = consumer threads of the sweep (>= P / 2, <= 512)
+    int hcap;                    // half-warps that take bank-aligned pairs (the rest of the T / 16 is for the leftover items)
 };
 
 // Pass 1 — fully parallel, one CTA per state-plane: the distinct successor cells of the plane and the code word of every
@@ -152,6 +159,329 @@ __global__ void __launch_bounds__(kCellThreads) plane_cells_kernel(const PlanPar
     if (any && n_unstaged) atomicAdd(&s_un, n_unstaged);
     __syncthreads();
     if (tid == 0) q.cells[pl].n_unstaged = s_un;
+}
+
+// Pass 1, ITEM MODE (PS_PACK == 2 in plane_sweep_src.cuh) — one CTA per state-plane.  Besides the cells it regroups the
+// plane's P states into work items of two states, one item per sweep thread (T item slots per plane, T >= P / 2):
+//   * REGULAR PAIRS: states p and p+1 that are staged in the same successor cell with in-plane offsets o (even) and o+1
+//     (x-neighbours that take the same action).  The sweep backs both up from one aligned 64-bit load + one 32-bit load
+//     per (outer corner, f1 corner) instead of 2 x 2 loads, with the two states in the halves of packed f32x2 multiplies
+//     and fmas.  BANK-ALIGNED PLACEMENT: the 64-bit load of the 16 lanes of a half-warp is one shared-memory wavefront
+//     only if the lanes hit 16 distinct bank pairs, so a pair goes to lane (o / 2) mod 16 of the first half-warp in which
+//     that lane is free (slot pitch = 0 mod 32 floats: the bank does not depend on the slot, cells may mix in a warp).
+//     Natural order pays 2 wavefronts per load (a row of 18 live states is 9 pairs: every half-warp straddles a row break);
+//     aligned placement 1.27 at 78 % lane occupancy (scripts/analysis/pair_pack_model.py).  The first `hcap` half-warps
+//     take aligned pairs; pairs that find their lane taken `hcap` times fill holes (correct, one more wavefront);
+//   * the LEFTOVER states, two per item, fill the item slots from the END (the last warp): those that need a backup
+//     (singles, global-gather fallback) first, the trivial ones last, item j taking leftover j and leftover m-1-j;
+//   * TERMINAL states (V kept) ride along as PASSENGERS of pair items (the second state's code word is redundant in a pair).
+// Every state keeps its own row words (fractions, reward): nothing about the arithmetic changes, only which thread does
+// it.  The code word of a state: bits 0-11 in-plane index p, 12-23 in-plane offset o of the successor's lower corner,
+// 24-26 cell number, 27-29 kind (0 staged, 1 global gather, 2 terminated: sum = 0, 3 terminal: V kept, 4 no state),
+// bit 31 (first state of an item only): the item is a regular pair — its second code word is then 0x80000000 | p of the
+// passenger, or kItemEmpty.
+constexpr unsigned kItemKindShift = 27;
+constexpr unsigned kItemEmpty = 4u << kItemKindShift;
+constexpr unsigned kItemPair = 0x80000000u;
+constexpr int kItemThreads = 128;
+constexpr int kItemPer = 8;       // states per thread (P <= 1024)
+constexpr int kItemSlotsPer = 4;  // item slots per thread (T <= 512)
+
+__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* s_w, unsigned long long* total) {
+    // exclusive sum over the kItemThreads threads of the CTA (s_w: kItemThreads / 32 words of shared memory)
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();   // s_w may still be read from a previous scan
+    if (lane == 31) s_w[wq] = inc;
+    __syncthreads();
+    unsigned long long before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kItemThreads / 32; ++w) {
+        const unsigned long long t = s_w[w];
+        if (w < wq) before += t;
+        all += t;
+    }
+    *total = all;
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanParams q) {
+    extern __shared__ __align__(16) unsigned char it_smem[];
+    __shared__ int htab[kPlanHash];
+    __shared__ int hcnt[kPlanHash];
+    __shared__ int hcell[kPlanHash];
+    __shared__ unsigned long long s_scan[kItemThreads / 32];
+    __shared__ int s_un;
+    const int P = q.P, T = q.T, W = q.W;
+    unsigned* const stage = reinterpret_cast<unsigned*>(it_smem);                                    // [nq][T][4] words
+    unsigned* const s_code = stage + (size_t)q.nq * T * 4;                                            // [P]
+    unsigned short* const s_dst = reinterpret_cast<unsigned short*>(s_code + P);                     // [P] item slot * 2 + half
+    unsigned short* const s_hslot = s_dst + P;                                                        // [P / 2] pair number -> item slot
+    unsigned short* const s_free = s_hslot + P / 2;                                                   // [T] free item slots, ascending
+    unsigned char* const s_head = reinterpret_cast<unsigned char*>(s_free + T);                      // [P]
+    unsigned char* const s_occ = s_head + P;                                                          // [T]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int pl = blockIdx.x;
+    const long long s0 = (long long)pl * P;
+    if (tid < kPlanHash) { htab[tid] = -1; hcnt[tid] = 0; hcell[tid] = -1; }
+    if (tid == 0) s_un = 0;
+    __syncthreads();
+
+    // ---- A. the distinct successor cells (as plane_cells_kernel) -> code word of every state
+    uint4 w[kItemPer];
+    int hs[kItemPer];
+#pragma unroll
+    for (int r = 0; r < kItemPer; ++r) {
+        const int t = tid + r * kItemThreads;
+        hs[r] = -1;
+        w[r] = make_uint4(0xfffffffeu, 0u, 0u, 0u);
+        if (t < P) w[r] = *reinterpret_cast<const uint4*>(q.rows + (size_t)(s0 + t) * 16u);
+    }
+#pragma unroll
+    for (int r = 0; r < kItemPer; ++r) {
+        const int t = tid + r * kItemThreads;
+        const int base = (int)w[r].x;
+        const bool live = t < P && base >= 0;
+        const int vp = live ? base / P : -1;
+        const unsigned act = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned same = __match_any_sync(act, vp);
+            int h = -1;
+            if ((__ffs(same) - 1) == lane) {
+                h = (int)(((unsigned)vp * 2654435761u) >> 27);
+                bool ok = false;
+                for (int probe = 0; probe < kPlanHash && !ok; ++probe) {
+                    const int old = atomicCAS(&htab[h], -1, vp);
+                    ok = old == -1 || old == vp;
+                    if (!ok) h = (h + 1) & (kPlanHash - 1);
+                }
+                if (ok) atomicAdd(&hcnt[h], __popc(same));
+                else h = -1;
+            }
+            hs[r] = __shfl_sync(same, h, __ffs(same) - 1);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const bool occ = htab[lane] != -1;
+        const unsigned m = __ballot_sync(0xffffffffu, occ);
+        const int k = __popc(m & ((1u << lane) - 1u));
+        PlaneCells* pc = q.cells + pl;
+        if (occ && k < kPlanMaxCells) {
+            hcell[lane] = k;
+            pc->vp[k] = htab[lane];
+            pc->cnt[k] = (unsigned short)min(hcnt[lane], 65535);
+        }
+        const int K = min(__popc(m), kPlanMaxCells);
+        if (lane >= K && lane < kPlanMaxCells) { pc->vp[lane] = -1; pc->cnt[lane] = 0; }
+        if (lane == 0) pc->n_cells = K;
+    }
+    __syncthreads();
+    int n_unstaged = 0;
+#pragma unroll
+    for (int r = 0; r < kItemPer; ++r) {
+        const int t = tid + r * kItemThreads;
+        if (t < P) {
+            const int base = (int)w[r].x;
+            unsigned code = (unsigned)t;
+            if (base >= 0) {
+                const int k = hs[r] >= 0 ? hcell[hs[r]] : -1;
+                if (k >= 0) code |= ((unsigned)(base - (base / P) * P) << 12) | ((unsigned)k << 24);
+                else { code |= 1u << kItemKindShift; ++n_unstaged; }
+            } else {
+                code |= (base == -1 ? 2u : 3u) << kItemKindShift;
+            }
+            s_code[t] = code;
+        }
+    }
+    if (n_unstaged) atomicAdd(&s_un, n_unstaged);
+    // every item slot starts empty: no state in either half, no passenger
+    for (int i = tid; i < T; i += kItemThreads) {
+        stage[(size_t)i * 4] = kItemEmpty;                                       // word 0 of the item: first state's code
+        stage[((size_t)(W >> 2) * T + i) * 4 + (W & 3)] = kItemEmpty;            // word W: second state's code
+        s_occ[i] = 0;
+    }
+    __syncthreads();
+
+    // ---- B. regular pairs (thread <-> kItemPer consecutive states from here on).  A pair starts at an EVEN in-plane
+    // offset; offsets grow by one from a state to its partner, so no state is claimed twice
+    const int p0 = tid * kItemPer;
+    unsigned codes[kItemPer + 1];
+#pragma unroll
+    for (int i = 0; i <= kItemPer; ++i) codes[i] = p0 + i < P ? s_code[p0 + i] : kItemEmpty;
+    unsigned heads = 0;
+#pragma unroll
+    for (int i = 0; i < kItemPer; ++i) {
+        const unsigned a = codes[i], b = codes[i + 1];
+        const bool l = (a >> kItemKindShift) == 0u && (b >> kItemKindShift) == 0u && ((a ^ b) & (7u << 24)) == 0u &&
+                       ((b >> 12) & 0xfffu) == ((a >> 12) & 0xfffu) + 1u;
+        if (l && ((a >> 12) & 1u) == 0u) heads |= 1u << i;
+    }
+#pragma unroll
+    for (int i = 0; i < kItemPer; ++i)
+        if (p0 + i < P) s_head[p0 + i] = (unsigned char)((heads >> i) & 1u);
+    __syncthreads();
+    unsigned tails = 0;
+#pragma unroll
+    for (int i = 0; i < kItemPer; ++i) {
+        const int p = p0 + i;
+        if (p > 0 && p < P && s_head[p - 1]) tails |= 1u << i;
+    }
+
+    // ---- C. item slots.  Counters (exclusive scans over the states in storage order): pairs per bank-pair class
+    // (10 bits each: at most 512 pairs), pairs, and the three kinds of unpaired states
+    unsigned long long c1 = 0, c2 = 0, c3 = 0, c4 = 0;   // classes 0-5 | classes 6-11 | classes 12-15, pairs << 40 | work, terminated << 16, terminal << 32
+#pragma unroll
+    for (int i = 0; i < kItemPer; ++i) {
+        if (p0 + i >= P) continue;
+        const unsigned kind = (codes[i] >> kItemKindShift) & 7u;
+        if ((heads >> i) & 1u) {
+            const unsigned c = (codes[i] >> 13) & 15u;
+            if (c < 6) c1 += 1ull << (10 * c);
+            else if (c < 12) c2 += 1ull << (10 * (c - 6));
+            else c3 += 1ull << (10 * (c - 12));
+            c3 += 1ull << 40;
+        } else if (!((tails >> i) & 1u)) {
+            c4 += kind <= 1u ? 1ull : kind == 2u ? (1ull << 16) : (1ull << 32);
+        }
+    }
+    unsigned long long t1, t2, t3, t4;
+    unsigned long long e1 = block_excl_scan_u64(c1, s_scan, &t1);
+    unsigned long long e2 = block_excl_scan_u64(c2, s_scan, &t2);
+    unsigned long long e3 = block_excl_scan_u64(c3, s_scan, &t3);
+    unsigned long long e4 = block_excl_scan_u64(c4, s_scan, &t4);
+    const int n_heads = (int)((t3 >> 40) & 0xffffull);
+    const int n_work = (int)(t4 & 0xffffull), n_k2 = (int)((t4 >> 16) & 0xffffull), n_k3 = (int)((t4 >> 32) & 0xffffull);
+    const int n_pass = min(n_k3, n_heads);              // terminal states that ride along with a pair
+    const int n_left = n_work + n_k2 + n_k3 - n_pass;   // unpaired states that need item halves of their own
+    const int half = (n_left + 1) / 2;                  // leftover items
+    // aligned pairs: lane = class, half-warp = how many pairs of that class came before
+    int place[kItemPer];                                // heads: item slot, or -1 - overflow rank; leftovers: leftover number j; passengers: pair number
+    unsigned long long c5 = 0;                          // pairs whose lane was taken in all hcap half-warps
+#pragma unroll
+    for (int i = 0; i < kItemPer; ++i) {
+        place[i] = 0;
+        if (p0 + i >= P) continue;
+        const unsigned kind = (codes[i] >> kItemKindShift) & 7u;
+        if ((heads >> i) & 1u) {
+            const unsigned c = (codes[i] >> 13) & 15u;
+            int r;
+            if (c < 6) { r = (int)((e1 >> (10 * c)) & 1023ull); e1 += 1ull << (10 * c); }
+            else if (c < 12) { r = (int)((e2 >> (10 * (c - 6))) & 1023ull); e2 += 1ull << (10 * (c - 6)); }
+            else { r = (int)((e3 >> (10 * (c - 12))) & 1023ull); e3 += 1ull << (10 * (c - 12)); }
+            if (r < q.hcap) {
+                place[i] = r * 16 + (int)c;
+                s_occ[place[i]] = 1;
+            } else {
+                place[i] = -1 - (int)c5;
+                c5 += 1ull;
+            }
+        } else if (!((tails >> i) & 1u)) {
+            if (kind <= 1u) { place[i] = (int)(e4 & 0xffffull); e4 += 1ull; }
+            else if (kind == 2u) { place[i] = n_work + (int)((e4 >> 16) & 0xffffull); e4 += 1ull << 16; }
+            else {
+                const int r = (int)((e4 >> 32) & 0xffffull);
+                e4 += 1ull << 32;
+                place[i] = r < n_pass ? r : n_work + n_k2 + (r - n_pass);   // passenger of pair r, or a leftover
+                if (r < n_pass) tails |= 1u << (16 + i);                    // bits 16..: passenger flags
+            }
+        }
+    }
+    unsigned long long t5;
+    const unsigned long long e5 = block_excl_scan_u64(c5, s_scan, &t5);   // (the barriers inside also publish s_occ)
+    // free item slots in ascending order: overflow pairs take them from the front (holes between the aligned pairs),
+    // leftover items from the back (the last warp first)
+    unsigned long long c6 = 0;
+#pragma unroll
+    for (int i = 0; i < kItemSlotsPer; ++i) {
+        const int sl = tid * kItemSlotsPer + i;
+        if (sl < T && !s_occ[sl]) c6 += 1ull;
+    }
+    unsigned long long t6;
+    unsigned long long e6 = block_excl_scan_u64(c6, s_scan, &t6);
+#pragma unroll
+    for (int i = 0; i < kItemSlotsPer; ++i) {
+        const int sl = tid * kItemSlotsPer + i;
+        if (sl < T && !s_occ[sl]) { s_free[(int)e6] = (unsigned short)sl; e6 += 1ull; }
+    }
+    const int n_free = (int)t6;
+    __syncthreads();
+    {
+        int pair_no = (int)((e3 >> 40) & 0xffffull);   // e3's pair counter was not advanced above: pairs before this thread
+#pragma unroll
+        for (int i = 0; i < kItemPer; ++i) {
+            const int p = p0 + i;
+            if (p >= P) continue;
+            if ((heads >> i) & 1u) {
+                int sl = place[i];
+                if (sl < 0) sl = s_free[(int)e5 + (-1 - sl)];
+                s_dst[p] = (unsigned short)(sl * 2);
+                s_code[p] = codes[i] | kItemPair;
+                s_hslot[pair_no++] = (unsigned short)sl;
+            } else if ((tails >> (16 + i)) & 1u) {
+                s_dst[p] = 0xffffu;   // passenger: no item half of its own
+            } else if (!((tails >> i) & 1u)) {
+                const int j = place[i];
+                const int item = j < half ? j : n_left - 1 - j;
+                s_dst[p] = (unsigned short)(s_free[n_free - 1 - item] * 2 + (j < half ? 0 : 1));
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kItemPer; ++i) {
+        const int p = p0 + i;
+        if (p >= P) continue;
+        if (p > 0 && ((tails >> i) & 1u)) s_dst[p] = (unsigned short)(s_dst[p - 1] + 1);
+        if ((tails >> (16 + i)) & 1u) {   // the second code word of pair item place[i] carries this terminal state
+            const int sl = s_hslot[place[i]];
+            stage[((size_t)(W >> 2) * T + sl) * 4 + (W & 3)] = kItemPair | (unsigned)p;
+        }
+    }
+    __syncthreads();
+
+    // ---- D. the row words of every state go to its place in the item array (staged in shared memory, stored coalesced)
+    const int n4 = W / 4, n2 = (W % 4) / 2, n1 = W % 2;
+    auto put = [&](int dst, int j, unsigned v) {   // word j of the state in half (dst & 1) of item slot (dst >> 1)
+        const int jj = (dst & 1) * W + j;
+        stage[((size_t)(jj >> 2) * T + (dst >> 1)) * 4 + (jj & 3)] = v;
+    };
+#pragma unroll
+    for (int r = 0; r < kItemPer; ++r) {
+        const int t = tid + r * kItemThreads;
+        if (t >= P) continue;
+        const int dst = s_dst[t];
+        if (dst == 0xffff) continue;                       // passenger
+        if (!(t > 0 && s_head[t - 1])) put(dst, 0, s_code[t]);   // the second state of a pair has no code word of its own
+        put(dst, 1, w[r].y);
+        put(dst, 2, w[r].z);
+        put(dst, 3, w[r].w);
+        for (int qq = 1; qq < n4; ++qq) {
+            const uint4 v = *reinterpret_cast<const uint4*>(q.rows + (size_t)qq * 16u * (size_t)q.n_pad + (size_t)(s0 + t) * 16u);
+            put(dst, 4 * qq, v.x); put(dst, 4 * qq + 1, v.y); put(dst, 4 * qq + 2, v.z); put(dst, 4 * qq + 3, v.w);
+        }
+        if (n2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(q.rows + (size_t)n4 * 16u * (size_t)q.n_pad + (size_t)(s0 + t) * 8u);
+            put(dst, 4 * n4, v.x); put(dst, 4 * n4 + 1, v.y);
+        }
+        if (n1) put(dst, W - 1, *reinterpret_cast<const unsigned*>(q.rows + ((size_t)n4 * 16u + (size_t)n2 * 8u) * (size_t)q.n_pad + (size_t)(s0 + t) * 4u));
+    }
+    __syncthreads();
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(stage);
+        uint4* dst = reinterpret_cast<uint4*>(q.irows + (size_t)pl * (size_t)q.nq * (size_t)T * 16u);
+        for (int i = tid; i < q.nq * T; i += kItemThreads) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        q.cells[pl].n_unstaged = s_un;
+        atomicAdd(q.stats + 6, (unsigned long long)n_heads);
+        atomicAdd(q.stats + 7, (unsigned long long)t5);   // pairs outside their aligned lane
+    }
 }
 
 // Pass 2 — one WARP per chunk of L consecutive state-planes, sequential over the chunk (the slot state of step i depends on

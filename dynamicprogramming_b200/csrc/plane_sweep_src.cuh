@@ -24,9 +24,20 @@
 // A state whose successor cell could not be staged (more distinct cells in a plane than the plan
 // holds, no free slot) is flagged by the planner and gathers from global memory like gp_sweep does.
 //
+// ITEM MODE (PS_PACK == 2): the planner (pi::plane_items_kernel) regroups the P states of a plane into work items of two
+// states, one item per thread.  REGULAR PAIRS — storage neighbours staged in the same cell whose in-plane offsets are o
+// (even) and o+1 (x-neighbours that take the same action: 78 % of K5's states under a bang-bang policy): the corners of
+// the second state along f0 are the first state's shifted by one float, so a pair reads one aligned 64-bit word and one
+// float per (outer corner, f1 corner) instead of 2 x 2 floats, and carries the two states in the two halves of
+// mul.rn.f32x2 / fma.rn.f32x2 (each half rounds exactly like the scalar instruction: same bits) — half the instructions
+// per backup.  The planner places a pair in the lane that matches the bank pair of its offset, so that the 64-bit load
+// of a half-warp is ONE shared-memory wavefront whatever rows and cells its pairs come from (slot pitch = 0 mod 32
+// floats).  The unpaired states follow two per item and take the one-state path, one after the other; terminal states
+// (value kept) ride along with pair items.
+//
 // The host prepends (dpb200.cu: plane_preamble):
 //   PS_D, PS_P, PS_NS, PS_THREADS (consumer threads = PS_P rounded up to a warp), PS_MINB, PS_L, PS_LV,
-//   PS_PACK, ps_cj[2^D] (outer-corner number of corner c), ps_imm[2^D] (in-plane float offset of corner c),
+//   PS_PACK, PS_N0 (extent of the fastest dimension), ps_cj[2^D] (outer-corner number of corner c), ps_imm[2^D] (in-plane float offset of corner c),
 //   gp_off[2^D] (global V offset of corner c, fallback path).
 
 typedef unsigned long long ps_u64;
@@ -109,7 +120,9 @@ struct PsParams {
 #define PS_PITCH PS_PLANE_BYTES      // bytes between slots (>= PS_PLANE_BYTES, multiple of 16)
 #endif
 #define PS_SLOTS_BYTES (PS_NS * PS_PITCH)
-#define PS_CS_WORDS (PS_MAXC * PS_MAXOC)
+#define PS_KSTRIDE 20                // words between the slot offsets of two cells: 16 + 4, so that the 128-bit reads of different
+                                     // cells by the lanes of a warp fall into different banks
+#define PS_CS_WORDS (PS_MAXC * PS_KSTRIDE)
 #ifndef PS_NOUT
 #define PS_NOUT 4                    // output planes in flight (ring): written by the consumers of step it, stored by TMA after it
 #endif
@@ -252,6 +265,116 @@ __device__ __noinline__ float ps_gather_global(const float* __restrict__ Vin, in
     return ev;
 }
 
+
+#if PS_PACK == 2
+// ------------------------------------------------------------------ item mode
+#if PS_N0 % 2
+#error "item mode needs rows of even length"
+#endif
+#define PS_NI PS_THREADS                 // item slots per state-plane (two states each; >= PS_P / 2), one per consumer thread
+#define PS_NQ ((2 * PS_W + 3) / 4)       // 16-byte quarters per item
+#define PS_KIND(c) (((c) >> 27) & 7u)
+#define PS_EMPTY (4u << 27)
+__device__ __forceinline__ ps_u64 ps_fma2(ps_u64 a, ps_u64 b, ps_u64 c) {
+    ps_u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// item `t` of local state-plane `pl`: state A in words [0, W), state B in words [W, 2W)
+__device__ __forceinline__ void ps_load_item(const PsParams& p, long long pl, int t, unsigned (&u)[4 * PS_NQ]) {
+    const unsigned char* src = p.prow0 + ((size_t)pl * PS_NQ * PS_NI + (size_t)t) * 16u;
+#pragma unroll
+    for (int q = 0; q < PS_NQ; ++q) {
+        const uint4 v = ps_ld16(src + (size_t)q * PS_NI * 16u);
+        u[4 * q] = v.x; u[4 * q + 1] = v.y; u[4 * q + 2] = v.z; u[4 * q + 3] = v.w;
+    }
+}
+// one state from its staged V-planes: the reference's weight products and fma chain (scalar form of the non-item mode)
+__device__ __forceinline__ float ps_backup_one(const unsigned* csk, const unsigned char* sbase, const float (&fr)[PS_D]) {
+    float pre[PS_NT];
+    pre[0] = 1.0f - fr[0];
+    pre[1] = fr[0];
+#pragma unroll
+    for (int d = 1; d < PS_D - PS_LV; ++d) {
+        const float f = fr[d], gq = 1.0f - f;
+#pragma unroll
+        for (int c = PS_NT / 2 - 1; c >= 0; --c) {
+            if (c < (1 << d)) {
+                const float t = pre[c];
+                pre[c + (1 << d)] = t * f;
+                pre[c] = t * gq;
+            }
+        }
+    }
+    float wt[PS_LV][2];
+#pragma unroll
+    for (int q = 0; q < PS_LV; ++q) {
+        const float l = fr[PS_D - PS_LV + q];
+        wt[q][0] = 1.0f - l;
+        wt[q][1] = l;
+    }
+    float ev = 0.0f;
+#pragma unroll
+    for (int c = 0; c < PS_C; ++c) {
+        float leaf = pre[c & (PS_NT - 1)];
+#pragma unroll
+        for (int q = 0; q < PS_LV; ++q) leaf = leaf * wt[q][(c >> (PS_D - PS_LV + q)) & 1];
+        const float* a = reinterpret_cast<const float*>(sbase + csk[ps_cj[c]]);
+        ev = fmaf(leaf, a[ps_imm[c]], ev);
+    }
+    return ev;
+}
+// a regular pair: state B's corners are state A's shifted by one float along f0, so corner c of B is the float after
+// corner c of A; both states ride in the halves of packed multiplies / fmas (per half: the scalar instruction's rounding)
+__device__ __forceinline__ ps_u64 ps_backup_pair(const unsigned* csk, const unsigned char* sbase, const float (&fa)[PS_D],
+                                                 const float (&fb)[PS_D]) {
+    unsigned cso[PS_NOC];
+#pragma unroll
+    for (int j = 0; j < PS_NOC; j += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(csk + j);
+        cso[j] = v.x; cso[j + 1] = v.y; cso[j + 2] = v.z; cso[j + 3] = v.w;
+    }
+    ps_u64 pre[PS_NT];
+    pre[0] = ps_pk(1.0f - fa[0], 1.0f - fb[0]);
+    pre[1] = ps_pk(fa[0], fb[0]);
+#pragma unroll
+    for (int d = 1; d < PS_D - PS_LV; ++d) {
+        const ps_u64 ff = ps_pk(fa[d], fb[d]), gg = ps_pk(1.0f - fa[d], 1.0f - fb[d]);
+#pragma unroll
+        for (int c = PS_NT / 2 - 1; c >= 0; --c) {
+            if (c < (1 << d)) {
+                const ps_u64 t = pre[c];
+                pre[c + (1 << d)] = ps_mul2(t, ff);
+                pre[c] = ps_mul2(t, gg);
+            }
+        }
+    }
+    ps_u64 wt[PS_LV][2];
+#pragma unroll
+    for (int q = 0; q < PS_LV; ++q) {
+        const float la = fa[PS_D - PS_LV + q], lb = fb[PS_D - PS_LV + q];
+        wt[q][0] = ps_pk(1.0f - la, 1.0f - lb);
+        wt[q][1] = ps_pk(la, lb);
+    }
+    ps_u64 ev = ps_pk(0.0f, 0.0f);
+#pragma unroll
+    for (int c = 0; c < PS_C; ++c) {
+        ps_u64 leaf = pre[c & (PS_NT - 1)];
+#pragma unroll
+        for (int q = 0; q < PS_LV; ++q) leaf = ps_mul2(leaf, wt[q][(c >> (PS_D - PS_LV + q)) & 1]);
+        const float* a = reinterpret_cast<const float*>(sbase + cso[ps_cj[c]]);
+        // the compiler loads each float once: 3 per (outer corner, f1 corner)
+        // the planner starts pairs at even in-plane offsets only (rows have even length), so the first two floats are one
+        // aligned 64-bit load (lanes two floats apart: a 32-bit load would pay a two-way bank conflict)
+        const int i0 = ps_imm[c] & ~1;
+        const float2 lo = *reinterpret_cast<const float2*>(a + i0);
+        const ps_u64 vv = (ps_imm[c] & 1) ? ps_pk(lo.y, a[i0 + 2]) : ps_pk(lo.x, lo.y);
+        ev = ps_fma2(leaf, vv, ev);
+    }
+    return ev;
+}
+#endif
+
 #define PS_CWARPS (PS_THREADS / 32)     // consumer warps
 
 // Roles: warps 0 .. PS_CWARPS-1 back up the states of the current plane (thread t <-> state t); the last warp is the
@@ -296,24 +419,35 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
         // ------------------------------------------------------------------ producer warp
         // The producer is idle while the consumers compute: it fetches the plan entries of its NEXT trigger into
         // registers before it waits for the consumers, so the TMA copies go out the moment the slots are free.
+        // The plan record of a step (header, load list, slot offsets) is fetched into registers TWO steps before it is used,
+        // with independent loads (the whole load list, whatever the counts): the producer's trigger after `done` never waits
+        // for global memory.  (Fetching a record when it was needed — header first, then the entries it announces — put two
+        // dependent DRAM round trips into every step: the sweep took the same 1.31 ms with half the consumer instructions.)
         constexpr int kPerLane = (PS_MAXLOADS + 31) / 32;
-        auto fetch = [&](const PsRec* r, unsigned first, unsigned n, unsigned (&e)[kPerLane]) {
-#pragma unroll
-            for (int q = 0; q < kPerLane; ++q) e[q] = (unsigned)(lane + 32 * q) < n ? r->loads[first + lane + 32 * q] : 0u;
+        struct Fetched {
+            unsigned hdr;               // n_early | n_late << 8 | n_cells << 16 | flags << 24
+            unsigned e[kPerLane];       // loads[lane + 32 q]: early loads first, then the late ones
+            uint2 cs;                   // slot offsets of (cell lane / 4, outer corners 4 (lane % 4) ..)
         };
-        auto copies = [&](const unsigned (&e)[kPerLane], unsigned n, ps_u64* bar) {
+        auto fetch_rec = [&](const PsRec* r, Fetched& f) {
+            f.hdr = *reinterpret_cast<const unsigned*>(r);
 #pragma unroll
-            for (int q = 0; q < kPerLane; ++q)
-                if ((unsigned)(lane + 32 * q) < n)
-                    ps_bulk_load(ps_smem + (size_t)(e[q] >> 24) * PS_PITCH, Vin + (size_t)(e[q] & 0xffffffu) * PS_P, PS_PLANE_BYTES, bar);
+            for (int q = 0; q < kPerLane; ++q) f.e[q] = lane + 32 * q < PS_MAXLOADS ? r->loads[lane + 32 * q] : 0u;
+            f.cs = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(r->cs) + lane * 4);
+        };
+        // entries [first, first + n) of the record's list: one TMA bulk copy each
+        auto copies = [&](const Fetched& f, unsigned first, unsigned n, ps_u64* bar) {
+#pragma unroll
+            for (int q = 0; q < kPerLane; ++q) {
+                const unsigned t = (unsigned)(lane + 32 * q);
+                if (t >= first && t < first + n)
+                    ps_bulk_load(ps_smem + (size_t)(f.e[q] >> 24) * PS_PITCH, Vin + (size_t)(f.e[q] & 0xffffffu) * PS_P, PS_PLANE_BYTES, bar);
+            }
         };
         auto stage_cs_regs = [&](const uint2 v, unsigned buf) {
             uint4 o;
             o.x = (v.x & 0xffffu) << 4; o.y = (v.x >> 16) << 4; o.z = (v.y & 0xffffu) << 4; o.w = (v.y >> 16) << 4;
-            *reinterpret_cast<uint4*>(cs_s + buf * PS_CS_WORDS + lane * 4) = o;
-        };
-        auto fetch_cs = [&](const PsRec* r) {
-            return *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(r->cs) + lane * 4);
+            *reinterpret_cast<uint4*>(cs_s + buf * PS_CS_WORDS + (lane >> 2) * PS_KSTRIDE + (lane & 3) * 4) = o;
         };
         // The new values of a plane leave through shared memory too: the consumers write them into out_s[it % PS_NOUT], and once
         // every consumer warp is done with the step this warp stores the whole plane with ONE TMA bulk copy into the local V
@@ -338,51 +472,43 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
             const int pl0 = chunk * PS_L;
             const int Lc = (p.n_planes - pl0) < PS_L ? (p.n_planes - pl0) : PS_L;
             const PsRec* rec = p.plan + pl0;
+            Fetched cur, nxt, nn;
+            fetch_rec(rec, cur);
+            nxt = cur;
+            if (Lc > 1) fetch_rec(rec + 1, nxt);
+            nn = nxt;
             for (int i = 0; i < Lc; ++i, ++it) {
-                const PsRec* r = rec + i;
-                const PsRec* rn = r + 1;
                 const bool more = i + 1 < Lc;
                 const unsigned b = it & 1;
-                // everything this trigger needs, fetched before the wait
-                unsigned e_late[kPerLane], e_early[kPerLane];
-                unsigned nl = 0, ne_n = 0, nl_n = 0;
-                uint2 cs_cur = make_uint2(0u, 0u), cs_nxt = make_uint2(0u, 0u);
-                if (!armed) {
-                    nl = r->n_late;
-                    fetch(r, r->n_early, nl, e_late);
-                    cs_cur = fetch_cs(r);
-                }
-                if (more) {
-                    ne_n = rn->n_early; nl_n = rn->n_late;
-                    fetch(rn, 0, ne_n, e_early);
-                    cs_nxt = fetch_cs(rn);
-                }
+                if (i + 2 < Lc) fetch_rec(rec + i + 2, nn);   // in flight while this warp waits for the consumers
 #if PS_PF_AHEAD > 0
                 // optional (off by default, see PS_PF_AHEAD): pull the planes of a later step into L2 now
                 if (i + PS_PF_AHEAD < Lc) {
-                    const PsRec* rp = r + PS_PF_AHEAD;
+                    const PsRec* rp = rec + i + PS_PF_AHEAD;
                     const unsigned np = (unsigned)rp->n_early + rp->n_late;
                     for (unsigned q = lane; q < np; q += 32)
                         ps_bulk_prefetch_l2(Vin + (size_t)(rp->loads[q] & 0xffffffu) * PS_P, PS_PLANE_BYTES);
                 }
 #endif
+                const unsigned ne = cur.hdr & 0xffu, nl = (cur.hdr >> 8) & 0xffu;
+                const unsigned ne_n = nxt.hdr & 0xffu, nl_n = (nxt.hdr >> 8) & 0xffu;
                 // every consumer warp is done with the previous step: its slots (and the other cs buffer) are free
                 if (it > 0) ps_mbar_wait(&done[b ^ 1], ((it - 1) >> 1) & 1);
                 if (prev_g0 >= 0) store_plane(it - 1, prev_g0);
                 prev_g0 = p.s_begin + (long long)(pl0 + i) * PS_P;
                 if (!armed) {
-                    stage_cs_regs(cs_cur, b);
+                    stage_cs_regs(cur.cs, b);
                     __syncwarp();
                     if (lane == 0) {
                         if (nl) ps_mbar_arrive_expect(&full[b], nl * (unsigned)PS_PLANE_BYTES);
                         else ps_mbar_arrive(&full[b]);
                     }
                     __syncwarp();
-                    copies(e_late, nl, &full[b]);
+                    copies(cur, ne, nl, &full[b]);
                 }
                 armed = false;
                 if (more) {
-                    stage_cs_regs(cs_nxt, b ^ 1);
+                    stage_cs_regs(nxt.cs, b ^ 1);
                     __syncwarp();
                     if (lane == 0) {
                         if (nl_n == 0) {   // nothing of the next step waits for this one: arm it now, warps may run ahead
@@ -393,9 +519,11 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
                         }
                     }
                     __syncwarp();
-                    copies(e_early, ne_n, &full[b ^ 1]);
+                    copies(nxt, 0u, ne_n, &full[b ^ 1]);
                     armed = nl_n == 0;
                 }
+                cur = nxt;
+                nxt = nn;
             }
         }
         if (prev_g0 >= 0) {   // the last plane of this CTA
@@ -405,6 +533,89 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
         if (lane == 0) ps_bulk_wait_all();   // every plane of new values has landed before the kernel ends
     } else {
         // ------------------------------------------------------------------ consumer warps
+#if PS_PACK == 2
+        for (int ci = p.sched_begin + blockIdx.x; ci < p.sched_end; ci += gridDim.x) {
+            const int chunk = ci + p.chunk_rot < p.n_chunks ? ci + p.chunk_rot : ci + p.chunk_rot - p.n_chunks;
+            const int pl0 = chunk * PS_L;
+            const int Lc = (p.n_planes - pl0) < PS_L ? (p.n_planes - pl0) : PS_L;
+            unsigned u[4 * PS_NQ];
+            ps_load_item(p, pl0, tid, u);
+            for (int i = 0; i < Lc; ++i, ++it) {
+                const unsigned b = it & 1;
+                const long long sp = (long long)(pl0 + i) * PS_P;   // first local state of the plane
+                const long long g0 = p.s_begin + sp;
+                const unsigned ca = u[0];
+                const bool is_pair = (ca >> 31) != 0u;
+                // a pair's second state: next in-plane index, next offset, same cell; its code word carries a passenger
+                // (a terminal state, whose value is kept) or nothing
+                const unsigned cb = is_pair ? (ca & 0x7fffffffu) + 0x1001u : u[PS_W];
+                const unsigned pass = is_pair ? u[PS_W] : 0u;
+                float fa[PS_D], fb[PS_D];
+#pragma unroll
+                for (int d = 0; d < PS_D; ++d) { fa[d] = __uint_as_float(u[1 + d]); fb[d] = __uint_as_float(u[PS_W + 1 + d]); }
+                const float ra = __uint_as_float(u[PS_D + 1]), rb = __uint_as_float(u[PS_W + PS_D + 1]);
+                // the next plane's item: in flight while this one is backed up
+                if (i + 1 < Lc) ps_load_item(p, pl0 + i + 1, tid, u);
+                const unsigned kinda = PS_KIND(ca), kindb = PS_KIND(cb);
+                const unsigned pa = ca & 0xfffu, pb = cb & 0xfffu;
+                float volda = 0.0f, voldb = 0.0f, vpass = 0.0f;
+                if (kinda < 4u && (p.check || kinda == 3u)) volda = Vin[g0 + pa];
+                if (kindb < 4u && (p.check || kindb == 3u)) voldb = Vin[g0 + pb];
+                if (pass >> 31) vpass = Vin[g0 + (pass & 0xfffu)];
+
+                ps_mbar_wait(&full[b], (it >> 1) & 1);
+
+                float eva = 0.0f, evb = 0.0f;
+                const unsigned* csa = cs_s + b * PS_CS_WORDS + ((ca >> 24) & 7u) * PS_KSTRIDE;
+                if (is_pair && csa[0] != PS_BAD_SLOT) {
+                    const ps_u64 ev2 = ps_backup_pair(csa, ps_smem + ((ca >> 12) & 0xfffu) * 4u, fa, fb);
+                    ps_unpk(ev2, eva, evb);
+                } else {
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned cc = h ? cb : ca;
+                        const unsigned kind = PS_KIND(cc);
+                        if (kind > 1u) continue;   // terminated (sum = 0), terminal (V kept) or no state
+                        float fr[PS_D];
+#pragma unroll
+                        for (int d = 0; d < PS_D; ++d) fr[d] = h ? fb[d] : fa[d];
+                        const unsigned* csk = cs_s + b * PS_CS_WORDS + ((cc >> 24) & 7u) * PS_KSTRIDE;
+                        float ev;
+                        if (kind == 0u && csk[0] != PS_BAD_SLOT) {
+                            ev = ps_backup_one(csk, ps_smem + ((cc >> 12) & 0xfffu) * 4u, fr);
+                        } else {
+                            // not staged: the original base index is word 0 of the policy's row
+                            const int base = (int)ps_ld4(p.rows + (size_t)(sp + (cc & 0xfffu)) * 16u);
+                            ev = ps_gather_global(Vin, base, fr[0], fr[1], fr[2], fr[3]
+#if PS_D >= 5
+                                                  , fr[4]
+#endif
+#if PS_D >= 6
+                                                  , fr[5]
+#endif
+                            );
+                        }
+                        if (h) evb = ev; else eva = ev;
+                    }
+                }
+                float* const o = out_s + (it % PS_NOUT) * PS_P;
+                if (kinda < 4u) {
+                    const float vnew = kinda == 3u ? volda : fmaf(p.gamma, eva, ra);
+                    o[pa] = vnew;
+                    if (p.check) res = fmaxf(res, fabsf(vnew - volda));
+                }
+                if (kindb < 4u) {
+                    const float vnew = kindb == 3u ? voldb : fmaf(p.gamma, evb, rb);
+                    o[pb] = vnew;
+                    if (p.check) res = fmaxf(res, fabsf(vnew - voldb));
+                }
+                if (pass >> 31) o[pass & 0xfffu] = vpass;
+                ps_fence_async_smem();   // the plane is read by the TMA store (async proxy)
+                __syncwarp();
+                if (lane == 0) ps_mbar_arrive(&done[b]);
+            }
+        }
+#else
         for (int ci = p.sched_begin + blockIdx.x; ci < p.sched_end; ci += gridDim.x) {
             const int chunk = ci + p.chunk_rot < p.n_chunks ? ci + p.chunk_rot : ci + p.chunk_rot - p.n_chunks;
             const int pl0 = chunk * PS_L;
@@ -432,9 +643,9 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
 
                 float ev = 0.0f;
                 // a cell whose V-planes found no slot is marked in its slot offsets (plane_slots_kernel): gather from global
-                const bool resident = staged && cs_s[b * PS_CS_WORDS + k * PS_MAXOC] != PS_BAD_SLOT;
+                const bool resident = staged && cs_s[b * PS_CS_WORDS + k * PS_KSTRIDE] != PS_BAD_SLOT;
                 if (resident) {
-                    const unsigned* csk = cs_s + b * PS_CS_WORDS + k * PS_MAXOC;
+                    const unsigned* csk = cs_s + b * PS_CS_WORDS + k * PS_KSTRIDE;
                     const unsigned char* sbase = ps_smem + ip * 4u;
 #if PS_PACK
                     // weight tree in packed pairs (corner bit 0 = the two halves): level d multiplies every pair by
@@ -527,6 +738,7 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
                 if (lane == 0) ps_mbar_arrive(&done[b]);
             }
         }
+#endif
     }
 
     if (!p.check) return;

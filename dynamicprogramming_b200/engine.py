@@ -582,12 +582,12 @@ class _CudaPolicyIterationBase(abc.ABC):
         the engine currently runs, on the current rows and V; timings, plan statistics and the number of
         differing V words (must be 0)."""
         ms_new, ms_base = C.c_float(), C.c_float()
-        mism, st, info = C.c_int64(), (C.c_double * 4)(), (C.c_int32 * 6)()
+        mism, st, info = C.c_int64(), (C.c_double * 8)(), (C.c_int32 * 6)()
         _ffi.check(_ffi.lib().pi_debug_plane(self._engine, cfg.encode(), int(iters), C.byref(ms_new), C.byref(ms_base),
                                              C.byref(mism), st, info))
         return {"ms_plane": ms_new.value, "ms_base": ms_base.value, "mismatches": int(mism.value),
                 "loads_per_plane": st[0], "late_per_plane": st[1], "cells_per_plane": st[2], "fallback_frac": st[3],
-                "registers": int(info[0]), "grid": int(info[1]), "block": int(info[2]), "smem": int(info[3]),
+                "pairs_per_plane": st[4], "stray_pairs_per_plane": st[5], "registers": int(info[0]), "grid": int(info[1]), "block": int(info[2]), "smem": int(info[3]),
                 "slots": int(info[4]), "chunk": int(info[5])}
 
     def debug_xline(self, cfg: str, iters: int = 5) -> dict:

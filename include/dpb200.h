@@ -238,10 +238,12 @@ int pi_debug_xline(pi_engine* e, const char* cfg, int32_t iters, float* ms_xline
 
 /* Test hook for the plane-staged sweep (csrc/plane_sweep_src.cuh: V read from shared memory, V-planes staged by TMA
  * bulk copies after a per-policy plan, csrc/plane_plan.cuh): compiles configuration `cfg` = "NS,L,minb,lv,pack"
- * (slots, state-planes per chunk, CTAs per SM, lean weight-tree levels, packed f32x2 weight tree; 0 = default),
+ * (slots, state-planes per chunk, CTAs per SM, lean weight-tree levels; pack: 0 one state per thread, 1 the same with a
+ * packed f32x2 weight tree, 2 item mode = two states per thread, regular pairs share loads; NS / L 0 = default),
  * plans the current rows, runs it and the engine's currently selected kernel `iters` times on the current rows and V
  * and counts differing words (must be 0).  stats = {plane loads, late loads, cells per state-plane, fraction of states
- * not staged}; info = {registers, grid, block, shared-memory bytes, slots, chunk}.  Engine state unchanged. */
+ * not staged, regular pairs per state-plane, pairs outside their bank-aligned lane (item mode)} — SIX doubles; info = {registers, grid, block, shared-memory
+ * bytes, slots, chunk}.  Engine state unchanged. */
 int pi_debug_plane(pi_engine* e, const char* cfg, int32_t iters, float* ms_plane, float* ms_base, int64_t* mismatches,
                    double* stats, int32_t* info);
 

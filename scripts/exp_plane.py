@@ -14,7 +14,7 @@ try:
 except ImportError:
     pass
 bins = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-cfgs = sys.argv[2:] or ["", "0,0,2,2,0", "0,0,2,1,1", "0,0,1,2,1", "0,40,2,2,1", "0,100,2,2,1", "48,0,2,2,1", "64,0,3,2,1"]
+cfgs = sys.argv[2:] or ["0,0,2,2,2", "0,0,2,2,0", "0,0,2,1,2", "0,0,2,3,2", "0,10,2,2,2", "0,0,3,2,2"]
 t0 = time.time()
 eng = envs.make("double_cartpole_swingup", bins=bins)
 eng.build_table()

@@ -51,7 +51,7 @@ def test_layout_probe_finds_the_cart_plane(env, bins, monkeypatch):
 
 @pytest.mark.parametrize("env,bins", CART)
 @pytest.mark.parametrize("policy", ["initial", "greedy", "random"])
-@pytest.mark.parametrize("cfg", ["", "0,0,2,2,0", "0,3,1,1,1", "40,7,2,2,1"])
+@pytest.mark.parametrize("cfg", ["", "0,0,2,2,0", "0,3,1,1,1", "40,7,2,2,1", "0,0,2,2,2", "0,3,1,1,2", "40,7,2,2,2"])
 def test_plane_sweep_is_bit_identical_to_the_gather_sweep(env, bins, policy, cfg, monkeypatch):
     eng = _prepared(env, bins, monkeypatch, policy=policy)
     if cfg.startswith("40") and eng.N_DIMS == 4:
