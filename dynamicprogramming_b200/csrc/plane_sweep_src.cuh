@@ -116,6 +116,9 @@ struct PsParams {
                                      // steps ahead -> 1.39, 1.44, 1.63, 1.45 ms per sweep vs 1.34 without: the extra plan reads
                                      // delay the producer's trigger and the prefetches compete with the copies)
 #endif
+#ifndef PS_ROW_PF
+#define PS_ROW_PF 3                  // steps ahead whose rows the producer prefetches into L2 (0: off)
+#endif
 #ifndef PS_PITCH
 #define PS_PITCH PS_PLANE_BYTES      // bytes between slots (>= PS_PLANE_BYTES, multiple of 16)
 #endif
@@ -481,6 +484,33 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
                 const bool more = i + 1 < Lc;
                 const unsigned b = it & 1;
                 if (i + 2 < Lc) fetch_rec(rec + i + 2, nn);   // in flight while this warp waits for the consumers
+#if PS_ROW_PF > 0
+                // The consumers load the rows of a plane one step before they use them — less than a DRAM round trip once a step
+                // takes about a microsecond (ncu: 21 % of the warp samples waited for those loads).  One bulk L2 prefetch per plane,
+                // PS_ROW_PF steps ahead (into the CTA's next chunk at the end of a chunk), turns them into L2 hits.
+                if (lane == 0) {
+                    int pf_pl = pl0 + i + PS_ROW_PF;
+                    if (i + PS_ROW_PF >= Lc) {
+                        const int cn = ci + (int)gridDim.x;
+                        pf_pl = -1;
+                        if (cn < p.sched_end) {
+                            const int chn = cn + p.chunk_rot < p.n_chunks ? cn + p.chunk_rot : cn + p.chunk_rot - p.n_chunks;
+                            pf_pl = chn * PS_L + (i + PS_ROW_PF - Lc);
+                            if (pf_pl >= p.n_planes) pf_pl = -1;
+                        }
+                    }
+                    if (pf_pl >= 0) {
+#if PS_PACK == 2
+                        ps_bulk_prefetch_l2(p.prow0 + (size_t)pf_pl * PS_NQ * PS_NI * 16u, PS_NQ * PS_NI * 16u);
+#else
+                        ps_bulk_prefetch_l2(p.prow0 + (size_t)pf_pl * PS_P * 16u, PS_P * 16u);
+#pragma unroll
+                        for (int q = 1; q < PS_N4; ++q)
+                            ps_bulk_prefetch_l2(p.rows + (size_t)q * 16u * (size_t)p.n_pad + (size_t)pf_pl * PS_P * 16u, PS_P * 16u);
+#endif
+                    }
+                }
+#endif
 #if PS_PF_AHEAD > 0
                 // optional (off by default, see PS_PF_AHEAD): pull the planes of a later step into L2 now
                 if (i + PS_PF_AHEAD < Lc) {

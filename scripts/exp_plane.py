@@ -26,11 +26,18 @@ d, ms = eng.sweeps(25)
 print("engine sweeps: %.4f ms/sweep" % (ms / 25), flush=True)
 out = []
 for cfg in cfgs:
+    # "cfg@K=V,K=V": environment knobs read when the sweep is compiled (e.g. DPB200_PLANE_ROWPF)
+    spec, _, envs_ = cfg.partition("@")
+    for kv in filter(None, envs_.split(";")):
+        k, _, v = kv.partition("=")
+        os.environ[k] = v
     try:
-        r = eng.debug_plane(cfg, iters=10)
+        r = eng.debug_plane(spec, iters=10)
     except Exception as ex:  # noqa: BLE001
         r = {"error": str(ex)[:300]}
     r["cfg"] = cfg
+    for kv in filter(None, envs_.split(";")):
+        os.environ.pop(kv.partition("=")[0], None)
     print(json.dumps(r), flush=True)
     out.append(r)
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
