@@ -178,8 +178,9 @@ __global__ void __launch_bounds__(kCellThreads) plane_cells_kernel(const PlanPar
 // Every state keeps its own row words (fractions, reward): nothing about the arithmetic changes, only which thread does
 // it.  The code word of a state: bits 0-11 in-plane index p, 12-23 in-plane offset o of the successor's lower corner,
 // 24-26 cell number, 27-29 kind (0 staged, 1 global gather, 2 terminated: sum = 0, 3 terminal: V kept, 4 no state),
-// bit 31 (first state of an item only): the item is a regular pair — its second code word is then 0x80000000 | p of the
-// passenger, or kItemEmpty.
+// bit 31 (first state of an item only): the item takes the pair path — bits 27-28 then say which halves hold a state
+// (0 both, 1 the first only, 2 the second only: a single with a dummy partner), the second state's code is the first's
+// plus one index and one offset, and the second code word is 0x80000000 | p of the passenger, or kItemEmpty.
 constexpr unsigned kItemKindShift = 27;
 constexpr unsigned kItemEmpty = 4u << kItemKindShift;
 constexpr unsigned kItemPair = 0x80000000u;
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     unsigned short* const s_dst = reinterpret_cast<unsigned short*>(s_code + P);                     // [P] item slot * 2 + half
     unsigned short* const s_hslot = s_dst + P;                                                        // [P / 2] pair number -> item slot
     unsigned short* const s_free = s_hslot + P / 2;                                                   // [T] free item slots, ascending
-    unsigned char* const s_head = reinterpret_cast<unsigned char*>(s_free + T);                      // [P]
-    unsigned char* const s_occ = s_head + P;                                                          // [T]
+    unsigned char* const s_flag = reinterpret_cast<unsigned char*>(s_free + T);                      // [P]
+    unsigned char* const s_occ = s_flag + P;                                                          // [T]
     const int tid = threadIdx.x, lane = tid & 31;
     const int pl = blockIdx.x;
     const long long s0 = (long long)pl * P;
@@ -324,78 +325,104 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     }
 #pragma unroll
     for (int i = 0; i < kItemPer; ++i)
-        if (p0 + i < P) s_head[p0 + i] = (unsigned char)((heads >> i) & 1u);
+        if (p0 + i < P) s_flag[p0 + i] = (unsigned char)((heads >> i) & 1u);
     __syncthreads();
     unsigned tails = 0;
 #pragma unroll
     for (int i = 0; i < kItemPer; ++i) {
         const int p = p0 + i;
-        if (p > 0 && p < P && s_head[p - 1]) tails |= 1u << i;
+        if (p > 0 && p < P && s_flag[p - 1]) tails |= 1u << i;
     }
+    __syncthreads();   // s_flag is rewritten below
 
-    // ---- C. item slots.  Counters (exclusive scans over the states in storage order): pairs per bank-pair class
-    // (10 bits each: at most 512 pairs), pairs, and the three kinds of unpaired states
-    unsigned long long c1 = 0, c2 = 0, c3 = 0, c4 = 0;   // classes 0-5 | classes 6-11 | classes 12-15, pairs << 40 | work, terminated << 16, terminal << 32
+    // ---- C. item slots.  Round 1 (one exclusive scan over the states in storage order, 12-bit counters): pairs, staged
+    // singles, other states that need a backup (global-gather fallback), terminated states, terminal states
+    enum { kHead = 0, kTail = 1, kSingle = 2, kWork = 3, kK2 = 4, kK3 = 5 };
+    int cat[kItemPer];
+    unsigned long long c0 = 0;
 #pragma unroll
     for (int i = 0; i < kItemPer; ++i) {
+        cat[i] = -1;
         if (p0 + i >= P) continue;
         const unsigned kind = (codes[i] >> kItemKindShift) & 7u;
-        if ((heads >> i) & 1u) {
-            const unsigned c = (codes[i] >> 13) & 15u;
-            if (c < 6) c1 += 1ull << (10 * c);
-            else if (c < 12) c2 += 1ull << (10 * (c - 6));
-            else c3 += 1ull << (10 * (c - 12));
-            c3 += 1ull << 40;
-        } else if (!((tails >> i) & 1u)) {
-            c4 += kind <= 1u ? 1ull : kind == 2u ? (1ull << 16) : (1ull << 32);
+        // a staged single can ride the pair path (below) unless the dummy in front of it would be state -1
+        const bool odd_at_0 = p0 + i == 0 && ((codes[i] >> 12) & 1u);
+        cat[i] = ((heads >> i) & 1u) ? kHead : ((tails >> i) & 1u) ? kTail : (kind == 0u && !odd_at_0) ? kSingle : kind <= 1u ? kWork : kind == 2u ? kK2 : kK3;
+        if (cat[i] != kTail) c0 += 1ull << (12 * (cat[i] == kHead ? 0 : cat[i] - 1));
+    }
+    unsigned long long t0;
+    unsigned long long e0 = block_excl_scan_u64(c0, s_scan, &t0);
+    const int n_heads = (int)(t0 & 0xfffull), n_single = (int)((t0 >> 12) & 0xfffull), n_gw = (int)((t0 >> 24) & 0xfffull);
+    const int n_k2 = (int)((t0 >> 36) & 0xfffull), n_k3 = (int)((t0 >> 48) & 0xfffull);
+    const int n_pass = min(n_k3, n_heads);              // terminal states that ride along with a pair
+    // SINGLES ON THE PAIR PATH: a staged single at offset o becomes a pair item with one dummy half — (single, dummy) when o
+    // is even, (dummy, single) starting at o - 1 when it is odd — and is placed bank-aligned like a pair: it fills lanes
+    // the pairs leave empty, and the one-state path (twice the shared-memory wavefronts per backup) is not run at all on
+    // a cart-pole plane.  As many singles as the T item slots allow (each takes a whole slot instead of half of one).
+    const int rest = n_gw + n_k2 + n_k3 - n_pass;
+    const int n_conv = max(0, min(n_single, 2 * T - 2 * n_heads - n_single - rest - 1));
+    const int n_left = n_single - n_conv + rest;        // states that share generic items, two each
+    const int half = (n_left + 1) / 2;
+    // Round 2: bank-pair class counts of the aligned items (pairs + converted singles), 10-bit counters
+    unsigned long long c1 = 0, c2 = 0, c3 = 0;          // classes 0-5 | 6-11 | 12-15
+    {
+        int sr = (int)((e0 >> 12) & 0xfffull);          // staged singles before this thread
+#pragma unroll
+        for (int i = 0; i < kItemPer; ++i) {
+            if (cat[i] == kSingle) { if (sr >= n_conv) cat[i] = kWork + 16; ++sr; }   // kWork + 16: an unconverted single
+            if (cat[i] == kHead || cat[i] == kSingle) {
+                const unsigned c = (codes[i] >> 13) & 15u;
+                if (c < 6) c1 += 1ull << (10 * c);
+                else if (c < 12) c2 += 1ull << (10 * (c - 6));
+                else c3 += 1ull << (10 * (c - 12));
+            }
         }
     }
-    unsigned long long t1, t2, t3, t4;
+    unsigned long long t1, t2, t3;
     unsigned long long e1 = block_excl_scan_u64(c1, s_scan, &t1);
     unsigned long long e2 = block_excl_scan_u64(c2, s_scan, &t2);
     unsigned long long e3 = block_excl_scan_u64(c3, s_scan, &t3);
-    unsigned long long e4 = block_excl_scan_u64(c4, s_scan, &t4);
-    const int n_heads = (int)((t3 >> 40) & 0xffffull);
-    const int n_work = (int)(t4 & 0xffffull), n_k2 = (int)((t4 >> 16) & 0xffffull), n_k3 = (int)((t4 >> 32) & 0xffffull);
-    const int n_pass = min(n_k3, n_heads);              // terminal states that ride along with a pair
-    const int n_left = n_work + n_k2 + n_k3 - n_pass;   // unpaired states that need item halves of their own
-    const int half = (n_left + 1) / 2;                  // leftover items
-    // aligned pairs: lane = class, half-warp = how many pairs of that class came before
-    int place[kItemPer];                                // heads: item slot, or -1 - overflow rank; leftovers: leftover number j; passengers: pair number
-    unsigned long long c5 = 0;                          // pairs whose lane was taken in all hcap half-warps
+    // aligned items: lane = class, half-warp = how many items of that class came before; the generic items keep the last
+    // half-warps to themselves
+    const int hcap = max(1, min(q.hcap, (T - half) / 16));
+    int place[kItemPer];                                // aligned items: item slot, or -1 - stray rank; generic: leftover number j; passengers: pair number
+    unsigned long long c5 = 0;                          // aligned items whose lane was taken in all hcap half-warps
+    {
+        int sr = (int)((e0 >> 12) & 0xfffull), gw = (int)((e0 >> 24) & 0xfffull), k2 = (int)((e0 >> 36) & 0xfffull), k3 = (int)((e0 >> 48) & 0xfffull);
 #pragma unroll
-    for (int i = 0; i < kItemPer; ++i) {
-        place[i] = 0;
-        if (p0 + i >= P) continue;
-        const unsigned kind = (codes[i] >> kItemKindShift) & 7u;
-        if ((heads >> i) & 1u) {
-            const unsigned c = (codes[i] >> 13) & 15u;
-            int r;
-            if (c < 6) { r = (int)((e1 >> (10 * c)) & 1023ull); e1 += 1ull << (10 * c); }
-            else if (c < 12) { r = (int)((e2 >> (10 * (c - 6))) & 1023ull); e2 += 1ull << (10 * (c - 6)); }
-            else { r = (int)((e3 >> (10 * (c - 12))) & 1023ull); e3 += 1ull << (10 * (c - 12)); }
-            if (r < q.hcap) {
-                place[i] = r * 16 + (int)c;
-                s_occ[place[i]] = 1;
-            } else {
-                place[i] = -1 - (int)c5;
-                c5 += 1ull;
-            }
-        } else if (!((tails >> i) & 1u)) {
-            if (kind <= 1u) { place[i] = (int)(e4 & 0xffffull); e4 += 1ull; }
-            else if (kind == 2u) { place[i] = n_work + (int)((e4 >> 16) & 0xffffull); e4 += 1ull << 16; }
-            else {
-                const int r = (int)((e4 >> 32) & 0xffffull);
-                e4 += 1ull << 32;
-                place[i] = r < n_pass ? r : n_work + n_k2 + (r - n_pass);   // passenger of pair r, or a leftover
-                if (r < n_pass) tails |= 1u << (16 + i);                    // bits 16..: passenger flags
+        for (int i = 0; i < kItemPer; ++i) {
+            place[i] = 0;
+            if (cat[i] == kHead || cat[i] == kSingle) {
+                const unsigned c = (codes[i] >> 13) & 15u;
+                int r;
+                if (c < 6) { r = (int)((e1 >> (10 * c)) & 1023ull); e1 += 1ull << (10 * c); }
+                else if (c < 12) { r = (int)((e2 >> (10 * (c - 6))) & 1023ull); e2 += 1ull << (10 * (c - 6)); }
+                else { r = (int)((e3 >> (10 * (c - 12))) & 1023ull); e3 += 1ull << (10 * (c - 12)); }
+                if (r < hcap) {
+                    place[i] = r * 16 + (int)c;
+                    s_occ[place[i]] = 1;
+                } else {
+                    place[i] = -1 - (int)c5;
+                    c5 += 1ull;
+                }
+                if (cat[i] == kSingle) ++sr;
+            } else if (cat[i] == kWork + 16) {
+                place[i] = sr - n_conv; ++sr;                              // unconverted singles first
+            } else if (cat[i] == kWork) {
+                place[i] = n_single - n_conv + gw; ++gw;
+            } else if (cat[i] == kK2) {
+                place[i] = n_single - n_conv + n_gw + k2; ++k2;
+            } else if (cat[i] == kK3) {
+                place[i] = k3 < n_pass ? k3 : n_single - n_conv + n_gw + n_k2 + (k3 - n_pass);   // passenger of pair k3, or a leftover
+                if (k3 < n_pass) cat[i] = kK3 + 16;                        // kK3 + 16: a passenger
+                ++k3;
             }
         }
     }
     unsigned long long t5;
     const unsigned long long e5 = block_excl_scan_u64(c5, s_scan, &t5);   // (the barriers inside also publish s_occ)
-    // free item slots in ascending order: overflow pairs take them from the front (holes between the aligned pairs),
-    // leftover items from the back (the last warp first)
+    // free item slots in ascending order: stray aligned items take them from the front (holes between the aligned ones),
+    // generic items from the back (the last warp first)
     unsigned long long c6 = 0;
 #pragma unroll
     for (int i = 0; i < kItemSlotsPer; ++i) {
@@ -411,25 +438,40 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     }
     const int n_free = (int)t6;
     __syncthreads();
+    // s_flag: where the code word of a state goes — 0 its own half, 1 nowhere (second state of a pair), 2 word 0 of the item
+    // although the state sits in the second half (a single behind a dummy), 3 the state is a passenger
     {
-        int pair_no = (int)((e3 >> 40) & 0xffffull);   // e3's pair counter was not advanced above: pairs before this thread
+        int pair_no = (int)(e0 & 0xfffull);            // pairs before this thread
 #pragma unroll
         for (int i = 0; i < kItemPer; ++i) {
             const int p = p0 + i;
             if (p >= P) continue;
-            if ((heads >> i) & 1u) {
+            unsigned char flag = 0;
+            if (cat[i] == kHead || cat[i] == kSingle) {
                 int sl = place[i];
                 if (sl < 0) sl = s_free[(int)e5 + (-1 - sl)];
-                s_dst[p] = (unsigned short)(sl * 2);
-                s_code[p] = codes[i] | kItemPair;
-                s_hslot[pair_no++] = (unsigned short)sl;
-            } else if ((tails >> (16 + i)) & 1u) {
-                s_dst[p] = 0xffffu;   // passenger: no item half of its own
-            } else if (!((tails >> i) & 1u)) {
+                if (cat[i] == kHead) {
+                    s_dst[p] = (unsigned short)(sl * 2);
+                    s_code[p] = (codes[i] & 0x07ffffffu) | kItemPair;                       // both halves valid
+                    s_hslot[pair_no++] = (unsigned short)sl;
+                } else if (((codes[i] >> 12) & 1u) == 0u) {
+                    s_dst[p] = (unsigned short)(sl * 2);
+                    s_code[p] = (codes[i] & 0x07ffffffu) | kItemPair | (1u << kItemKindShift);   // (single, dummy)
+                } else {
+                    s_dst[p] = (unsigned short)(sl * 2 + 1);
+                    s_code[p] = ((codes[i] & 0x07ffffffu) - 0x1001u) | kItemPair | (2u << kItemKindShift);   // (dummy, single): one index, one offset back
+                    flag = 2;
+                }
+            } else if (cat[i] == kTail) {
+                flag = 1;
+            } else if (cat[i] == kK3 + 16) {
+                flag = 3;
+            } else {
                 const int j = place[i];
                 const int item = j < half ? j : n_left - 1 - j;
                 s_dst[p] = (unsigned short)(s_free[n_free - 1 - item] * 2 + (j < half ? 0 : 1));
             }
+            s_flag[p] = flag;
         }
     }
     __syncthreads();
@@ -437,8 +479,8 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     for (int i = 0; i < kItemPer; ++i) {
         const int p = p0 + i;
         if (p >= P) continue;
-        if (p > 0 && ((tails >> i) & 1u)) s_dst[p] = (unsigned short)(s_dst[p - 1] + 1);
-        if ((tails >> (16 + i)) & 1u) {   // the second code word of pair item place[i] carries this terminal state
+        if (cat[i] == kTail) s_dst[p] = (unsigned short)(s_dst[p - 1] + 1);
+        if (cat[i] == kK3 + 16) {   // the second code word of pair item place[i] carries this terminal state
             const int sl = s_hslot[place[i]];
             stage[((size_t)(W >> 2) * T + sl) * 4 + (W & 3)] = kItemPair | (unsigned)p;
         }
@@ -455,9 +497,11 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     for (int r = 0; r < kItemPer; ++r) {
         const int t = tid + r * kItemThreads;
         if (t >= P) continue;
+        const int flag = s_flag[t];
+        if (flag == 3) continue;                           // passenger
         const int dst = s_dst[t];
-        if (dst == 0xffff) continue;                       // passenger
-        if (!(t > 0 && s_head[t - 1])) put(dst, 0, s_code[t]);   // the second state of a pair has no code word of its own
+        if (flag == 0) put(dst, 0, s_code[t]);
+        else if (flag == 2) put(dst & ~1, 0, s_code[t]);
         put(dst, 1, w[r].y);
         put(dst, 2, w[r].z);
         put(dst, 3, w[r].w);
@@ -480,7 +524,8 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     if (tid == 0) {
         q.cells[pl].n_unstaged = s_un;
         atomicAdd(q.stats + 6, (unsigned long long)n_heads);
-        atomicAdd(q.stats + 7, (unsigned long long)t5);   // pairs outside their aligned lane
+        atomicAdd(q.stats + 7, (unsigned long long)t5);   // aligned items outside their lane
+        atomicAdd(q.stats + 8, (unsigned long long)n_conv);   // singles on the pair path
     }
 }
 

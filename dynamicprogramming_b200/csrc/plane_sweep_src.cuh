@@ -574,11 +574,15 @@ extern "C" __global__ void __launch_bounds__(PS_THREADS + 32, PS_MINB) ps_sweep(
                 const unsigned b = it & 1;
                 const long long sp = (long long)(pl0 + i) * PS_P;   // first local state of the plane
                 const long long g0 = p.s_begin + sp;
-                const unsigned ca = u[0];
-                const bool is_pair = (ca >> 31) != 0u;
-                // a pair's second state: next in-plane index, next offset, same cell; its code word carries a passenger
-                // (a terminal state, whose value is kept) or nothing
-                const unsigned cb = is_pair ? (ca & 0x7fffffffu) + 0x1001u : u[PS_W];
+                const unsigned c0 = u[0];
+                const bool is_pair = (c0 >> 31) != 0u;
+                // An item on the pair path: the second state has the next in-plane index and the next offset in the same cell;
+                // bits 27-28 say which halves hold a state (0 both, 1 the first only, 2 the second only — a single with a
+                // dummy partner whose result is dropped); the second code word carries a passenger (a terminal state, whose
+                // value is kept) or nothing.
+                const unsigned vm = (c0 >> 27) & 3u;
+                const unsigned ca = is_pair ? (c0 & 0x87ffffffu) | (vm == 2u ? PS_EMPTY : 0u) : c0;
+                const unsigned cb = is_pair ? ((c0 & 0x07ffffffu) + 0x1001u) | (vm == 1u ? PS_EMPTY : 0u) : u[PS_W];
                 const unsigned pass = is_pair ? u[PS_W] : 0u;
                 float fa[PS_D], fb[PS_D];
 #pragma unroll

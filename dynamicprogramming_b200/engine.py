@@ -587,7 +587,7 @@ class _CudaPolicyIterationBase(abc.ABC):
                                              C.byref(mism), st, info))
         return {"ms_plane": ms_new.value, "ms_base": ms_base.value, "mismatches": int(mism.value),
                 "loads_per_plane": st[0], "late_per_plane": st[1], "cells_per_plane": st[2], "fallback_frac": st[3],
-                "pairs_per_plane": st[4], "stray_pairs_per_plane": st[5], "registers": int(info[0]), "grid": int(info[1]), "block": int(info[2]), "smem": int(info[3]),
+                "pairs_per_plane": st[4], "stray_pairs_per_plane": st[5], "singles_paired_per_plane": st[6], "registers": int(info[0]), "grid": int(info[1]), "block": int(info[2]), "smem": int(info[3]),
                 "slots": int(info[4]), "chunk": int(info[5])}
 
     def debug_xline(self, cfg: str, iters: int = 5) -> dict:

@@ -242,7 +242,7 @@ int pi_debug_xline(pi_engine* e, const char* cfg, int32_t iters, float* ms_xline
  * packed f32x2 weight tree, 2 item mode = two states per thread, regular pairs share loads; NS / L 0 = default),
  * plans the current rows, runs it and the engine's currently selected kernel `iters` times on the current rows and V
  * and counts differing words (must be 0).  stats = {plane loads, late loads, cells per state-plane, fraction of states
- * not staged, regular pairs per state-plane, pairs outside their bank-aligned lane (item mode)} — SIX doubles; info = {registers, grid, block, shared-memory
+ * not staged, regular pairs per state-plane, items outside their bank-aligned lane, single states on the pair path (item mode)} — SEVEN doubles; info = {registers, grid, block, shared-memory
  * bytes, slots, chunk}.  Engine state unchanged. */
 int pi_debug_plane(pi_engine* e, const char* cfg, int32_t iters, float* ms_plane, float* ms_base, int64_t* mismatches,
                    double* stats, int32_t* info);

@@ -9,6 +9,6 @@ import sys, json
 for l in sys.stdin:
     l = l.strip()
     if l.startswith('{'):
-        d = json.loads(l); print(d.get('cfg'), 'ms %.4f base %.4f mism %s loads %.1f late %.2f pairs %.1f regs %s slots %s' % (d.get('ms_plane', 0), d.get('ms_base', 0), d.get('mismatches'), d.get('loads_per_plane', 0), d.get('late_per_plane', 0), d.get('pairs_per_plane', 0), d.get('registers'), d.get('slots')), d.get('error', ''))
+        d = json.loads(l); print(d.get('cfg'), 'ms %.4f base %.4f mism %s loads %.1f late %.2f pairs %.1f stray %.2f singles-paired %.1f regs %s slots %s' % (d.get('ms_plane', 0), d.get('ms_base', 0), d.get('mismatches'), d.get('loads_per_plane', 0), d.get('late_per_plane', 0), d.get('pairs_per_plane', 0), d.get('stray_pairs_per_plane', 0), d.get('singles_paired_per_plane', 0), d.get('registers'), d.get('slots')), d.get('error', ''))
     else: print(l[:200])
 "
