@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One sweep family on a small grid, for compute-sanitizer (tests/test_gpu_sanitizer.py):
     compute-sanitizer --tool memcheck --error-exitcode 1 python scripts/sanitize_target.py <family>
-families: aot | gp_single | gp_pair | xline | persistent | plane | plane_small | lookup"""
+families: aot | gp_single | gp_pair | xline | persistent | plane | plane_small | plane_scalar | plane_items_small | lookup"""
 import os
 import sys
 from pathlib import Path
@@ -18,6 +18,8 @@ cfg = {
     "persistent": {"DPB200_PLANE": "off", "DPB200_XLINE": "off", "DPB200_PAIR": "off", "DPB200_PERSIST": "on"},
     "plane": {"DPB200_PLANE": "force"},
     "plane_small": {"DPB200_PLANE": "force:34,5,2,1,1"},
+    "plane_scalar": {"DPB200_PLANE": "force:0,0,2,2,0"},
+    "plane_items_small": {"DPB200_PLANE": "force:34,5,2,2,2"},
     "lookup": {},
 }[family]
 os.environ.update(cfg)
@@ -32,7 +34,7 @@ eng = envs.make(env, bins=bins)
 eng.build_table()
 info = eng.eval_kernel_info()["kernel"]
 want = {"aot": "eval_sweep_kernel", "gp_single": "gp_sweep", "gp_pair": "gp_sweep", "xline": "xl_sweep",
-        "persistent": "eval_persistent_kernel", "plane": "ps_sweep", "plane_small": "ps_sweep", "lookup": ""}[family]
+        "persistent": "eval_persistent_kernel", "plane": "ps_sweep", "plane_small": "ps_sweep", "plane_scalar": "ps_sweep", "plane_items_small": "ps_sweep", "lookup": ""}[family]
 assert want in info, (family, info)
 eng.sweeps(3)
 eng.policy_improvement()

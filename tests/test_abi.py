@@ -106,8 +106,12 @@ def test_jit_sweep_kernels_compile_for_sm_100a_without_a_gpu():
         assert lib.pi_xline_compile_check(D, bins, cfg, __import__("ctypes").byref(n)) == _ffi.PI_OK, lib.pi_last_error()
         assert n.value > 10_000
     assert lib.pi_xline_compile_check(6, 20, b"pair:64,8", None) == _ffi.PI_OK
-    # the plane-staged sweep (TMA-staged V-planes): 6-D and 4-D, scalar and packed weight tree
+    # the plane-staged sweep (TMA-staged V-planes): 6-D and 4-D; one state per thread with scalar / packed weight tree,
+    # and item mode (two states per thread)
     assert lib.pi_xline_compile_check(6, 20, b"plane:0,0,2,2,0", None) == _ffi.PI_OK, lib.pi_last_error()
+    assert lib.pi_xline_compile_check(6, 20, b"plane:", None) == _ffi.PI_OK, lib.pi_last_error()
+    assert lib.pi_xline_compile_check(6, 20, b"plane:0,0,2,2,2", None) == _ffi.PI_OK, lib.pi_last_error()
+    assert lib.pi_xline_compile_check(4, 12, b"plane:0,0,2,1,2", None) == _ffi.PI_OK, lib.pi_last_error()
     assert lib.pi_xline_compile_check(4, 20, b"plane:0,0,2,1,1", None) == _ffi.PI_OK, lib.pi_last_error()
     assert lib.pi_xline_compile_check(6, 15, b"plane:0,0,2,2,0", None) == _ffi.PI_ERR_INVALID   # a 15 x 15 plane is not a multiple of 16 bytes
     assert lib.pi_xline_compile_check(4, 40, b"plane:0,0,2,2,0", None) == _ffi.PI_ERR_INVALID   # a 40 x 40 plane has more than 1024 states

@@ -50,7 +50,7 @@ def _mixed_policy_pair(env, bins, ref_runner, sweeps=50):
 @pytest.mark.parametrize("env,bins,kernels", [("double_pendulum_swingup", 50, "default"), ("double_pendulum_swingup", 50, "gather"),
                                               ("double_pendulum_swingup", 50, "aot"), ("double_cartpole_swingup", 20, "default"),
                                               ("double_cartpole_swingup", 20, "gather"), ("double_cartpole_swingup", 20, "plane"),
-                                              ("double_cartpole_swingup", 20, "aot")])
+                                              ("double_cartpole_swingup", 20, "plane_one"), ("double_cartpole_swingup", 20, "aot")])
 def test_improvement_and_sweep_at_baseline_size_match_the_reference(env, bins, kernels, ref_runner, monkeypatch):
     """K4 / K5: the improvement pass (policy bits) and one sweep under the resulting mixed policy (V bits), with the
     kernel the engine selects by default — the one bench.py times — and with each sweep family pinned."""
@@ -58,7 +58,9 @@ def test_improvement_and_sweep_at_baseline_size_match_the_reference(env, bins, k
         monkeypatch.setenv("DPB200_PLANE", "off")
         monkeypatch.setenv("DPB200_XLINE", "off")
     elif kernels == "plane":
-        monkeypatch.setenv("DPB200_PLANE", "force")
+        monkeypatch.setenv("DPB200_PLANE", "force")              # item mode (two states per thread)
+    elif kernels == "plane_one":
+        monkeypatch.setenv("DPB200_PLANE", "force:0,0,2,2,0")    # one state per thread
     elif kernels == "aot":
         monkeypatch.setenv("DPB200_PLANE", "off")
         monkeypatch.setenv("DPB200_XLINE", "off")
@@ -67,8 +69,8 @@ def test_improvement_and_sweep_at_baseline_size_match_the_reference(env, bins, k
     info = eng.eval_kernel_info()
     if kernels == "default" and env == "double_cartpole_swingup":
         assert "ps_sweep" in info["kernel"] or "gp_sweep" in info["kernel"], info     # the JIT sweeps bench.py times
-    if kernels == "plane" and env == "double_cartpole_swingup":
-        assert info["plane"], info
+    if kernels in ("plane", "plane_one") and env == "double_cartpole_swingup":
+        assert info["plane"] and ("pack 2" in info["kernel"]) == (kernels == "plane"), info
     if kernels == "aot":
         assert "eval_sweep_kernel" in info["kernel"], info
     _, pol = eng.download()

@@ -17,8 +17,8 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 SAN = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
 
-FAMILIES = ["aot", "gp_single", "gp_pair", "xline", "persistent", "plane", "plane_small", "lookup"]
-CASES = [("memcheck", f) for f in FAMILIES] + [("synccheck", f) for f in ("plane", "plane_small", "persistent", "xline")] + \
+FAMILIES = ["aot", "gp_single", "gp_pair", "xline", "persistent", "plane", "plane_small", "plane_scalar", "plane_items_small", "lookup"]
+CASES = [("memcheck", f) for f in FAMILIES] + [("synccheck", f) for f in ("plane", "plane_small", "plane_scalar", "persistent", "xline")] + \
         [("racecheck", f) for f in ("aot", "gp_single", "xline", "persistent")]
 
 
