@@ -1178,8 +1178,9 @@ __global__ void __launch_bounds__(1024) count_reduce_kernel(Ctl* ctl, const unsi
 template <int D>
 __global__ void __launch_bounds__(kBlock) compact_rows_kernel(const unsigned char* table, unsigned char* rows,
                                                               const int* policy, long long n_local,
-                                                              long long n_pad, unsigned long long* regular) {
-    const long long s = (long long)blockIdx.x * kBlock + threadIdx.x;
+                                                              long long n_pad, unsigned long long* regular, long long s_first = 0) {
+    // states [s_first, n_local): s_first a multiple of the warp size (the regularity counters look at aligned groups)
+    const long long s = s_first + (long long)blockIdx.x * kBlock + threadIdx.x;
     int base = PI_ROW_ABSORBING;
     if (s < n_local) {
         constexpr int W = Row<D>::W;

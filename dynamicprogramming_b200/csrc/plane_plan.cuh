@@ -59,6 +59,8 @@ struct PlanParams {
     unsigned long long* stats;   // out (atomic): [0] plane loads, [1] late loads, [2] fallback states, [3] live states,
                                  //               [4] staged cells, [5] state-planes
     int n_planes;                // local state-planes
+    int pl_begin;                // this launch plans the state-planes [pl_begin, pl_end) (pl_begin a multiple of L): a policy upload
+    int pl_end;                  // is planned range by range while the rest is still on its way (pi_upload_policy_local)
     int L;                       // state-planes per chunk
     int P;                       // states per plane
     int NS;                      // shared-memory slots of the sweep
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(kCellThreads) plane_cells_kernel(const PlanPar
     __shared__ int hcnt[kPlanHash];
     __shared__ int hcell[kPlanHash];            // hash entry -> cell number (or -1: does not fit)
     const int tid = threadIdx.x, lane = tid & 31;
-    const int pl = blockIdx.x;
+    const int pl = q.pl_begin + blockIdx.x;
     const long long s0 = (long long)pl * q.P;
     if (tid < kPlanHash) { htab[tid] = -1; hcnt[tid] = 0; hcell[tid] = -1; }
     __syncthreads();
@@ -185,7 +187,6 @@ constexpr unsigned kItemKindShift = 27;
 constexpr unsigned kItemEmpty = 4u << kItemKindShift;
 constexpr unsigned kItemPair = 0x80000000u;
 constexpr int kItemThreads = 128;
-constexpr int kItemPer = 8;       // states per thread (P <= 1024)
 constexpr int kItemSlotsPer = 4;  // item slots per thread (T <= 512)
 
 __device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* s_w, unsigned long long* total) {
@@ -211,7 +212,9 @@ __device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long 
     return before + inc - v;
 }
 
-__global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanParams q) {
+// KP = states per thread (the smallest power of two with KP * kItemThreads >= P)
+template <int KP>
+__global__ void __launch_bounds__(kItemThreads, 8) plane_items_kernel(const PlanParams q) {
     extern __shared__ __align__(16) unsigned char it_smem[];
     __shared__ int htab[kPlanHash];
     __shared__ int hcnt[kPlanHash];
@@ -227,26 +230,26 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     unsigned char* const s_flag = reinterpret_cast<unsigned char*>(s_free + T);                      // [P]
     unsigned char* const s_occ = s_flag + P;                                                          // [T]
     const int tid = threadIdx.x, lane = tid & 31;
-    const int pl = blockIdx.x;
+    const int pl = q.pl_begin + blockIdx.x;
     const long long s0 = (long long)pl * P;
     if (tid < kPlanHash) { htab[tid] = -1; hcnt[tid] = 0; hcell[tid] = -1; }
     if (tid == 0) s_un = 0;
     __syncthreads();
 
     // ---- A. the distinct successor cells (as plane_cells_kernel) -> code word of every state
-    uint4 w[kItemPer];
-    int hs[kItemPer];
+    int w0[KP];   // base word of the row (the other words are read again in phase D: registers matter more than L2 hits)
+    int hs[KP];
 #pragma unroll
-    for (int r = 0; r < kItemPer; ++r) {
+    for (int r = 0; r < KP; ++r) {
         const int t = tid + r * kItemThreads;
         hs[r] = -1;
-        w[r] = make_uint4(0xfffffffeu, 0u, 0u, 0u);
-        if (t < P) w[r] = *reinterpret_cast<const uint4*>(q.rows + (size_t)(s0 + t) * 16u);
+        w0[r] = -2;
+        if (t < P) w0[r] = *reinterpret_cast<const int*>(q.rows + (size_t)(s0 + t) * 16u);
     }
 #pragma unroll
-    for (int r = 0; r < kItemPer; ++r) {
+    for (int r = 0; r < KP; ++r) {
         const int t = tid + r * kItemThreads;
-        const int base = (int)w[r].x;
+        const int base = w0[r];
         const bool live = t < P && base >= 0;
         const int vp = live ? base / P : -1;
         const unsigned act = __ballot_sync(0xffffffffu, live);
@@ -285,10 +288,10 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     __syncthreads();
     int n_unstaged = 0;
 #pragma unroll
-    for (int r = 0; r < kItemPer; ++r) {
+    for (int r = 0; r < KP; ++r) {
         const int t = tid + r * kItemThreads;
         if (t < P) {
-            const int base = (int)w[r].x;
+            const int base = w0[r];
             unsigned code = (unsigned)t;
             if (base >= 0) {
                 const int k = hs[r] >= 0 ? hcell[hs[r]] : -1;
@@ -309,27 +312,27 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     }
     __syncthreads();
 
-    // ---- B. regular pairs (thread <-> kItemPer consecutive states from here on).  A pair starts at an EVEN in-plane
+    // ---- B. regular pairs (thread <-> KP consecutive states from here on).  A pair starts at an EVEN in-plane
     // offset; offsets grow by one from a state to its partner, so no state is claimed twice
-    const int p0 = tid * kItemPer;
-    unsigned codes[kItemPer + 1];
+    const int p0 = tid * KP;
+    unsigned codes[KP + 1];
 #pragma unroll
-    for (int i = 0; i <= kItemPer; ++i) codes[i] = p0 + i < P ? s_code[p0 + i] : kItemEmpty;
+    for (int i = 0; i <= KP; ++i) codes[i] = p0 + i < P ? s_code[p0 + i] : kItemEmpty;
     unsigned heads = 0;
 #pragma unroll
-    for (int i = 0; i < kItemPer; ++i) {
+    for (int i = 0; i < KP; ++i) {
         const unsigned a = codes[i], b = codes[i + 1];
         const bool l = (a >> kItemKindShift) == 0u && (b >> kItemKindShift) == 0u && ((a ^ b) & (7u << 24)) == 0u &&
                        ((b >> 12) & 0xfffu) == ((a >> 12) & 0xfffu) + 1u;
         if (l && ((a >> 12) & 1u) == 0u) heads |= 1u << i;
     }
 #pragma unroll
-    for (int i = 0; i < kItemPer; ++i)
+    for (int i = 0; i < KP; ++i)
         if (p0 + i < P) s_flag[p0 + i] = (unsigned char)((heads >> i) & 1u);
     __syncthreads();
     unsigned tails = 0;
 #pragma unroll
-    for (int i = 0; i < kItemPer; ++i) {
+    for (int i = 0; i < KP; ++i) {
         const int p = p0 + i;
         if (p > 0 && p < P && s_flag[p - 1]) tails |= 1u << i;
     }
@@ -338,10 +341,10 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     // ---- C. item slots.  Round 1 (one exclusive scan over the states in storage order, 12-bit counters): pairs, staged
     // singles, other states that need a backup (global-gather fallback), terminated states, terminal states
     enum { kHead = 0, kTail = 1, kSingle = 2, kWork = 3, kK2 = 4, kK3 = 5 };
-    int cat[kItemPer];
+    int cat[KP];
     unsigned long long c0 = 0;
 #pragma unroll
-    for (int i = 0; i < kItemPer; ++i) {
+    for (int i = 0; i < KP; ++i) {
         cat[i] = -1;
         if (p0 + i >= P) continue;
         const unsigned kind = (codes[i] >> kItemKindShift) & 7u;
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     {
         int sr = (int)((e0 >> 12) & 0xfffull);          // staged singles before this thread
 #pragma unroll
-        for (int i = 0; i < kItemPer; ++i) {
+        for (int i = 0; i < KP; ++i) {
             if (cat[i] == kSingle) { if (sr >= n_conv) cat[i] = kWork + 16; ++sr; }   // kWork + 16: an unconverted single
             if (cat[i] == kHead || cat[i] == kSingle) {
                 const unsigned c = (codes[i] >> 13) & 15u;
@@ -385,12 +388,12 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     // aligned items: lane = class, half-warp = how many items of that class came before; the generic items keep the last
     // half-warps to themselves
     const int hcap = max(1, min(q.hcap, (T - half) / 16));
-    int place[kItemPer];                                // aligned items: item slot, or -1 - stray rank; generic: leftover number j; passengers: pair number
+    int place[KP];                                // aligned items: item slot, or -1 - stray rank; generic: leftover number j; passengers: pair number
     unsigned long long c5 = 0;                          // aligned items whose lane was taken in all hcap half-warps
     {
         int sr = (int)((e0 >> 12) & 0xfffull), gw = (int)((e0 >> 24) & 0xfffull), k2 = (int)((e0 >> 36) & 0xfffull), k3 = (int)((e0 >> 48) & 0xfffull);
 #pragma unroll
-        for (int i = 0; i < kItemPer; ++i) {
+        for (int i = 0; i < KP; ++i) {
             place[i] = 0;
             if (cat[i] == kHead || cat[i] == kSingle) {
                 const unsigned c = (codes[i] >> 13) & 15u;
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     {
         int pair_no = (int)(e0 & 0xfffull);            // pairs before this thread
 #pragma unroll
-        for (int i = 0; i < kItemPer; ++i) {
+        for (int i = 0; i < KP; ++i) {
             const int p = p0 + i;
             if (p >= P) continue;
             unsigned char flag = 0;
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kItemPer; ++i) {
+    for (int i = 0; i < KP; ++i) {
         const int p = p0 + i;
         if (p >= P) continue;
         if (cat[i] == kTail) s_dst[p] = (unsigned short)(s_dst[p - 1] + 1);
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
         stage[((size_t)(jj >> 2) * T + (dst >> 1)) * 4 + (jj & 3)] = v;
     };
 #pragma unroll
-    for (int r = 0; r < kItemPer; ++r) {
+    for (int r = 0; r < KP; ++r) {
         const int t = tid + r * kItemThreads;
         if (t >= P) continue;
         const int flag = s_flag[t];
@@ -502,9 +505,10 @@ __global__ void __launch_bounds__(kItemThreads) plane_items_kernel(const PlanPar
         const int dst = s_dst[t];
         if (flag == 0) put(dst, 0, s_code[t]);
         else if (flag == 2) put(dst & ~1, 0, s_code[t]);
-        put(dst, 1, w[r].y);
-        put(dst, 2, w[r].z);
-        put(dst, 3, w[r].w);
+        {
+            const uint4 v = *reinterpret_cast<const uint4*>(q.rows + (size_t)(s0 + t) * 16u);
+            put(dst, 1, v.y); put(dst, 2, v.z); put(dst, 3, v.w);
+        }
         for (int qq = 1; qq < n4; ++qq) {
             const uint4 v = *reinterpret_cast<const uint4*>(q.rows + (size_t)qq * 16u * (size_t)q.n_pad + (size_t)(s0 + t) * 16u);
             put(dst, 4 * qq, v.x); put(dst, 4 * qq + 1, v.y); put(dst, 4 * qq + 2, v.z); put(dst, 4 * qq + 3, v.w);
@@ -539,9 +543,9 @@ __global__ void __launch_bounds__(kSlotWarps * 32) plane_slots_kernel(const Plan
     __shared__ int s_cs[kSlotWarps][kPlanMaxCells * kPlanMaxOC];
     __shared__ unsigned s_early[kSlotWarps][kPlanMaxLoads], s_late[kSlotWarps][kPlanMaxLoads];
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int chunk = blockIdx.x * kSlotWarps + wq;
+    const int chunk = q.pl_begin / q.L + blockIdx.x * kSlotWarps + wq;
     const int pl0 = chunk * q.L;
-    if (pl0 >= q.n_planes) return;
+    if (pl0 >= q.pl_end) return;
     const int Lc = min(q.L, q.n_planes - pl0);
     int* slot_vp = s_slot_vp[wq];
     int* slot_used = s_slot_used[wq];

@@ -108,3 +108,34 @@ def test_plane_autotune_never_changes_results(monkeypatch):
         assert runs[mode][2] == runs["off"][2]
         np.testing.assert_array_equal(runs[mode][0], runs["off"][0])
         np.testing.assert_array_equal(bits(runs[mode][1]), bits(runs["off"][1]))
+
+
+@pytest.mark.parametrize("env,bins,plane", [("double_cartpole_swingup", 8, "force"), ("double_cartpole_swingup", 10, "force:0,3,2,2,0"),
+                                            ("cartpole", 14, "force")])
+def test_pipelined_policy_upload_equals_the_serial_upload(env, bins, plane, monkeypatch):
+    """pi_upload_policy_local with the plane-staged sweep ready sends the slice in pieces and compacts / plans each piece
+    while the next one is on the link (plan kernels over state-plane ranges): same rows, same plan, same V bits as one
+    copy followed by one compaction and one plan — and as the gather sweep."""
+    res = {}
+    P = None
+    for mode in ("serial", "pipelined", "gather"):
+        monkeypatch.setenv("DPB200_PLANE", "off" if mode == "gather" else plane)
+        monkeypatch.setenv("DPB200_UPLOAD", "serial" if mode == "serial" else "auto")
+        eng = envs.make(env, bins=bins)
+        eng.build_table()
+        if mode != "gather":
+            assert "ps_sweep" in eng.eval_kernel_info()["kernel"]
+        eng.sweeps(5)
+        if P is None:
+            rng = np.random.default_rng(11)
+            eng.policy_improvement()
+            P = np.where(rng.random(eng.n_states) < 0.1, rng.integers(0, eng.n_actions, eng.n_states), eng.download()[1]).astype(np.int32)
+        for rep in range(2):   # twice: the second upload starts while nothing of the first is pending
+            eng.upload_policy_local(eng.to_internal_order(P))
+            eng.sweeps(26)
+        v, p = eng.download()
+        res[mode] = (bits(v).copy(), p.copy())
+        eng.close()
+    for mode in ("pipelined", "gather"):
+        np.testing.assert_array_equal(res[mode][0], res["serial"][0])
+        np.testing.assert_array_equal(res[mode][1], res["serial"][1])
