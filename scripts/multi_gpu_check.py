@@ -33,6 +33,9 @@ GP2 = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:64,8,2,8,0"}
 # the plane-staged sweep (TMA-staged V-planes; needs plane-aligned shard boundaries), default and with few slots / ragged chunks
 PL = {"DPB200_PLANE": "force"}
 PL2 = {"DPB200_PLANE": "force:40,7,2,2,1"}
+# ... "force" is item mode (two states per thread); one state per thread, and item mode with few slots / ragged chunks
+PL0 = {"DPB200_PLANE": "force:0,0,2,2,0"}
+PL3 = {"DPB200_PLANE": "force:40,7,2,2,2"}
 # the gather sweep with the opt-in DMA exchange (boundary part, copy engines, interior part) instead of in-kernel peer stores,
 # and both JIT sweeps over NCCL send/recv
 GP1d = {"DPB200_XLINE": "off", "DPB200_PAIR": "force:128,8,2,8,1", "DPB200_EXCHANGE": "dma"}
@@ -42,7 +45,8 @@ cases = [("cartpole", 12, 4, {}), ("mountain_car", 60, None, {}), ("double_pendu
          ("double_cartpole_swingup", 8, 2, XL), ("cartpole_swingup", 12, 3, XL4),
          ("double_cartpole_swingup", 7, 2, GP1), ("cartpole_swingup", 11, 3, GP1), ("double_cartpole", 6, 2, GP2),
          ("double_cartpole_swingup", 8, 3, PL), ("cartpole", 12, 4, PL), ("double_cartpole", 6, 2, PL2),
-         ("double_cartpole_swingup", 10, 2, PL2), ("double_cartpole_swingup", 8, 3, PLn), ("double_cartpole_swingup", 7, 2, GP1d)]
+         ("double_cartpole_swingup", 10, 2, PL2), ("double_cartpole_swingup", 8, 3, PLn), ("double_cartpole_swingup", 7, 2, GP1d),
+         ("double_cartpole_swingup", 8, 3, PL0), ("double_cartpole_swingup", 10, 2, PL3), ("cartpole_swingup", 12, 3, PL3)]
 ok = True
 for env, bins, max_pi, engine_env in cases:
     for k in ("DPB200_FAST_DIM", "DPB200_XLINE", "DPB200_PAIR", "DPB200_PLANE", "DPB200_EXCHANGE"):
