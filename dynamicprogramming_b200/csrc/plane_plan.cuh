@@ -424,8 +424,9 @@ __global__ void __launch_bounds__(kItemThreads, 8) plane_items_kernel(const Plan
     }
     unsigned long long t5;
     const unsigned long long e5 = block_excl_scan_u64(c5, s_scan, &t5);   // (the barriers inside also publish s_occ)
-    // free item slots in ascending order: stray aligned items take them from the front (holes between the aligned ones),
-    // generic items from the back (the last warp first)
+    // free item slots in ascending order: generic items take them from the back (the last warp first), stray aligned items
+    // the ones just before — the last half-warps are the emptiest, so a stray there rarely shares a bank with the rightful
+    // owner of its class, and the strays of a plane cost one or two half-warps their conflict-free loads instead of five
     unsigned long long c6 = 0;
 #pragma unroll
     for (int i = 0; i < kItemSlotsPer; ++i) {
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(kItemThreads, 8) plane_items_kernel(const Plan
             unsigned char flag = 0;
             if (cat[i] == kHead || cat[i] == kSingle) {
                 int sl = place[i];
-                if (sl < 0) sl = s_free[(int)e5 + (-1 - sl)];
+                if (sl < 0) sl = s_free[n_free - 1 - half - ((int)e5 + (-1 - sl))];
                 if (cat[i] == kHead) {
                     s_dst[p] = (unsigned short)(sl * 2);
                     s_code[p] = (codes[i] & 0x07ffffffu) | kItemPair;                       // both halves valid
