@@ -73,7 +73,7 @@ struct PlanParams {
     int W;                       // words per row (D + 2)
     int nq;                      // 16-byte quarters per item: ceil(2 W / 4)
     int T;                       // item slots per state-plane = consumer threads of the sweep (>= P / 2, <= 512)
-    int hcap;                    // half-warps that take bank-aligned pairs (the rest of the T / 16 is for the leftover items)
+    int hcap;                    // half-warps that may take bank-aligned items (T / 16; the kernel keeps the last ones free for generic items)
 };
 
 // Pass 1 — fully parallel, one CTA per state-plane: the distinct successor cells of the plane and the code word of every
@@ -172,10 +172,15 @@ __global__ void __launch_bounds__(kCellThreads) plane_cells_kernel(const PlanPar
 //     only if the lanes hit 16 distinct bank pairs, so a pair goes to lane (o / 2) mod 16 of the first half-warp in which
 //     that lane is free (slot pitch = 0 mod 32 floats: the bank does not depend on the slot, cells may mix in a warp).
 //     Natural order pays 2 wavefronts per load (a row of 18 live states is 9 pairs: every half-warp straddles a row break);
-//     aligned placement 1.27 at 78 % lane occupancy (scripts/analysis/pair_pack_model.py).  The first `hcap` half-warps
-//     take aligned pairs; pairs that find their lane taken `hcap` times fill holes (correct, one more wavefront);
-//   * the LEFTOVER states, two per item, fill the item slots from the END (the last warp): those that need a backup
-//     (singles, global-gather fallback) first, the trivial ones last, item j taking leftover j and leftover m-1-j;
+//     aligned placement 1.27 at 78 % lane occupancy (scripts/analysis/pair_pack_model.py).  An item that finds its lane
+//     taken in every half-warp ("stray": 5 of 205 per K5 plane) takes a free lane of the last, emptiest half-warps —
+//     correct anywhere, it only risks a bank conflict with the rightful owner of its class;
+//   * STAGED SINGLES (no partner: the neighbour takes another action, or the offset is odd) take the same path with a DUMMY
+//     partner — (single, dummy) at an even offset, (dummy, single) one offset back at an odd one — and are placed like
+//     pairs, as many as the T slots allow (a single then costs a whole slot instead of half of one);
+//   * the LEFTOVER states (global-gather fallback, terminated rows, singles and terminal states that found no seat), two
+//     per generic item, fill the free slots from the END: those that need a backup first, the trivial ones last, item j
+//     taking leftover j and leftover m-1-j; the sweep runs its one-state path twice for such an item;
 //   * TERMINAL states (V kept) ride along as PASSENGERS of pair items (the second state's code word is redundant in a pair).
 // Every state keeps its own row words (fractions, reward): nothing about the arithmetic changes, only which thread does
 // it.  The code word of a state: bits 0-11 in-plane index p, 12-23 in-plane offset o of the successor's lower corner,
